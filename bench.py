@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- U1 block-sparse Contract GFLOP/s (fp64) at chi=4096 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--chi 4096]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `Contract(T1, T2)` of workload C3a: legs v = gauss_u1(chi,-20,19,6.0) and
+p = {+1,-1}; T1[(a,s);(t,b)] stored as [a,t,s,b] (labels [0,2,1,3], needs the block relayout), T2[(t,b);(u,c)]
+(labels [2,3,4,5]); 42 matched sectors at chi=4096, 2.74 GFLOP algorithmic (sum_q 2 m_q k_q n_q).
+The step runs: family-2 block relayout of T1 -> family-3 grouped DMMA GEMM (plan cached, as in any loop
+that contracts the same bond structure repeatedly, e.g. iTEBD / DMRG sweeps).
+
+JSON line keys follow the driver contract: value (device-timed, inputs resident in HBM), e2e (host buffers,
+H2D + Contract + D2H), roofline (grouped GEMM vs FP64 peak measured live), roofline_relayout (HBM),
+cpu_baseline (oracle port on the host cores, bounded sample), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "U1 block-sparse Contract GFLOP/s (fp64) at chi=4096"
+UNIT = "GFLOP/s"
+
+
+def c3a_specs(chi):
+    from oracle import tor10_oracle as orc  # generator of the synthetic legs only (no arithmetic)
+    v = orc.gauss_u1_qnums(chi, -20, 19, 6.0).tolist()
+    p = [[1], [-1]]
+    u1 = [["U1", 0]]
+    A = {"bonds": [{"dim": chi, "btype": -1, "qnums": v, "syms": u1}, {"dim": 2, "btype": 1, "qnums": p, "syms": u1},
+                   {"dim": 2, "btype": -1, "qnums": p, "syms": u1}, {"dim": chi, "btype": 1, "qnums": v, "syms": u1}],
+         "rowrank": 2, "labels": [0, 2, 1, 3]}
+    B = {"bonds": [{"dim": 2, "btype": -1, "qnums": p, "syms": u1}, {"dim": chi, "btype": -1, "qnums": v, "syms": u1},
+                   {"dim": 2, "btype": 1, "qnums": p, "syms": u1}, {"dim": chi, "btype": 1, "qnums": v, "syms": u1}],
+         "rowrank": 2, "labels": [2, 3, 4, 5]}
+    return A, B
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def cpu_port_run(chi, budget_s, max_reps):
+    """The oracle (vectorised numpy relayout + torch.matmul per sector, all host threads) on workload C3a."""
+    import torch
+    from helpers import osym
+    from oracle import tor10_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    A, B = c3a_specs(chi)
+    oa, ob = osym(A, seed=1003), osym(B, seed=1004)
+    mm = lambda x, y: torch.matmul(torch.from_numpy(x), torch.from_numpy(y)).numpy()  # noqa: E731
+    flops = None
+    times = []
+    t_end = time.time() + budget_s
+    while len(times) < max_reps and (time.time() < t_end or len(times) < 2):
+        t0 = time.perf_counter()
+        oc = orc.contract_sym(oa, ob, matmul=mm)
+        times.append(time.perf_counter() - t0)
+        if flops is None:
+            # out sector q pairs with A' and B' sectors of equal charge; A' is [m_q, k_q], out is [m_q, n_q]
+            aprime = oa.clone().permute([0, 2, 1, 3], rowrank=2)
+            from oracle.tor10_oracle import build_blockmap
+            bm = build_blockmap(aprime.bonds, aprime.braket, 2)
+            kq = {tuple(q): s[1] for q, s in zip(bm.block_qnums.tolist(), bm.shapes)}
+            flops = sum(2.0 * blk.shape[0] * blk.shape[1] * kq[tuple(q)]
+                        for q, blk in zip(oc.bm.block_qnums.tolist(), oc.blocks) if tuple(q) in kq)
+    return flops, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chi", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="warmup + steps only (for ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = "C3a: U1 rank-4 x rank-4 blockform Contract, chi=%d, d=2, gauss_u1(-20..19, sigma 6), fp64" % args.chi
+
+    # ------------------------------------------------------------------ reference arm -----
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        flops, times = cpu_port_run(args.chi, budget_s=max(20.0, 0.6 * (args.steps + args.warmup)),
+                                    max_reps=args.steps + args.warmup)
+        timed = times[min(args.warmup, len(times) - 1):] or times
+        ms = 1e3 * float(np.mean(timed))
+        val = flops / (ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "note": "reference CPU path restated (oracle port: numpy relayout + "
+                           "torch.matmul per sector); the unmodified Python reference cannot travel to the GPU box "
+                           "and needs ~60-80 s per operand relayout at this size (SURVEY 6)"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%d full Contract calls of the workload" % len(timed)},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm -----------
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import tor10_b200 as T
+    from helpers import psym
+    from tor10_b200 import _plan, parallel
+
+    if world > 1:
+        parallel.enable()
+    A, B = c3a_specs(args.chi)
+    a = psym(T, A, seed=1003, device=dev)
+    b = psym(T, B, seed=1004, device=dev)
+    plan = _plan.get_contract_plan(a, b)
+    flops = plan.flops_total                       # algorithmic, whole job
+    flush = torch.empty(256 * 1024 * 1024 // 8, device=dev, dtype=torch.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, n, pre=None):
+        """n calls, each bracketed by its own CUDA events; L2 flushed (256 MiB write) between calls."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for s, e in evs:
+            if pre is not None:
+                pre()
+            flush.fill_(1.0)
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    out_holder = [None]
+
+    def step():
+        out_holder[0] = T.Contract(a, b)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if args.profile_only:
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            step()
+        torch.cuda.synchronize()
+        return
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    per_step = timed_loop(step, args.steps)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_local = float(np.sum(per_step))
+    if world > 1:
+        tt = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    else:
+        ms_total = ms_local
+    ms_per_step = ms_total / args.steps
+    value = flops / (ms_per_step * 1e-3) / 1e9
+
+    # ---- stage timings on this rank's share (roofline of the dominant kernel) ---------------
+    A_arena, B_arena = a._arena_tensor(), b._arena_tensor()
+    dt = a.dtype
+    Ap = torch.empty(plan.rel_a.packed.size, device=dev, dtype=dt) if plan.rel_a is not None else A_arena
+    Bp = torch.empty(plan.rel_b.packed.size, device=dev, dtype=dt) if plan.rel_b is not None else B_arena
+    Cc = plan.Lo.new_arena(dt, zero=True)
+    if plan.rel_a is not None:
+        plan.rel_a.run(A_arena, Ap)
+    if plan.rel_b is not None:
+        plan.rel_b.run(B_arena, Bp)
+    nrep = max(10, min(args.steps, 50))
+    t_gemm = timed_loop(lambda: plan.gemm.run(Ap, Bp, Cc), nrep)
+    t_rel = timed_loop(lambda: plan.rel_a.run(A_arena, Ap), nrep) if plan.rel_a is not None else [0.0]
+    gemm_ms, rel_ms = float(np.mean(t_gemm)), float(np.mean(t_rel))
+    rel_bytes = 2.0 * 8.0 * plan.rel_a.moved_elems if plan.rel_a is not None else 0.0
+
+    # ---- end to end through the public API with HOST buffers -----------------------------------
+    hA = A_arena.cpu().pin_memory()
+    hB = B_arena.cpu().pin_memory()
+    hC = torch.empty(plan.Lo.arena_elems + 16, dtype=dt).pin_memory()
+
+    def e2e_step():
+        a._arena.copy_(hA, non_blocking=True)
+        b._arena.copy_(hB, non_blocking=True)
+        c = T.Contract(a, b)
+        hC.copy_(c._arena, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t_e2e = timed_loop(e2e_step, max(5, min(args.steps, 20)))
+    barrier()
+    e2e_ms = float(np.mean(t_e2e))
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- FP64 peak, measured live (MEASURED_PEAKS.json carries no fp64 figure) -------------------
+    import ctypes
+    lib = T._lib.load()
+    tf = ctypes.c_double(0.0)
+    T._lib.check(lib.t10_probe_f64_peak(1, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
+    dmma_probe = tf.value
+    T._lib.check(lib.t10_probe_f64_peak(0, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
+    dfma_probe = tf.value
+    n = 8192
+    x = torch.rand((n, n), device=dev, dtype=torch.float64)
+    y = torch.rand((n, n), device=dev, dtype=torch.float64)
+    torch.matmul(x, y)
+    best = 1e9
+    for _ in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch.matmul(x, y)
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    dgemm_tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    del x, y
+    peak_tf = max(dgemm_tf, dmma_probe)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    share = plan.gemm.flops / flops if flops else 1.0
+    gemm_tf = plan.gemm.flops / (gemm_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "sectors": int(plan.Lo.nsec), "algorithmic_gflop": flops / 1e9,
+                   "nnz_per_operand": int(a._layout.nnz), "tile_cfg": plan.gemm.tile_cfg,
+                   "parallelism": "sectors sharded over %d GPU(s), NCCL gather" % world if world > 1 else "1 GPU",
+                   "l2": "flushed between steps (256 MiB write); every step timed by its own CUDA event pair",
+                   "plan": "cached (block maps, relayout tables, tile table built once outside the timed region)"},
+        "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int((hA.numel() + hB.numel()) * 8), "d2h_bytes_per_step": int(hC.numel() * 8)},
+        "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
+                                          + 1)),
+        "roofline": {"kernel": "k_ggemm_f64 (grouped DMMA GEMM)", "bound": "tensor", "achieved": gemm_tf,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
+                     "traffic": None, "ms": gemm_ms, "rank_share_of_flops": share,
+                     "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
+                                    "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "
+                                    "fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe)},
+        "roofline_relayout": {"kernel": "k_relayout_blocks", "bound": "hbm",
+                              "achieved": rel_bytes / (rel_ms * 1e-3) / 1e9 if rel_ms else None, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": rel_bytes / (rel_ms * 1e-3) / 1e9 / hbm_peak if rel_ms else None,
+                              "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src},
+        "clocks": clocks, "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cf, ctimes = cpu_port_run(args.chi, budget_s=12.0, max_reps=20)
+        ct = float(np.mean(ctimes[1:] or ctimes))
+        line["cpu_baseline"] = {"value": cf / ct / 1e9, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d full Contract calls of the same workload by the oracle (numpy "
+                                          "vectorised relayout + torch.matmul per sector)" % len(ctimes[1:] or ctimes)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

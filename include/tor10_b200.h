@@ -1,0 +1,169 @@
+/*
+ * tor10_b200.h -- C-ABI of the B200 (sm_100a) kernels behind tor10's block-sparse
+ * contraction path.  Built as tor10_b200/lib/libtor10_b200.so (nvcc, no torch, no
+ * Python in the signatures: plain pointers, sizes and an opaque stream handle).
+ *
+ * Each entry point replaces one interpreted-Python / torch call site of the reference
+ * (kaihsin/Tor10, paths relative to /root/reference):
+ *
+ *   family 1 (integer, bit-exact)
+ *     t10_fuse_qnums        Bond.combine / UniTensor.GetTotalQnums   Bond.py:310-421, UniTensor.py:2859-2868
+ *     t10_blockmap_build    UniTensor.__init__ symmetric branch      UniTensor.py:393-441, Bond.py:13-28, :423-447
+ *     t10_unravel           _fx_decompress_idx                        UniTensor.py:24-29
+ *     t10_relayout_tables   index algebra of Contiguous()             UniTensor.py:2108-2120
+ *   family 2 (HBM-bound data movement)
+ *     t10_relayout_blocks   element loop of Contiguous()              UniTensor.py:2108-2129
+ *                           (gather form = GetBlock non-contiguous    UniTensor.py:3255-3273)
+ *     t10_permute_dense     Tensor.contiguous() / tensordot's copy    UniTensor.py:2057, :2144, :3769
+ *     t10_diag_scale        torch.diag + tensordot with a diagonal    UniTensor.py:3756-3765
+ *   family 3 (FP64 DMMA / FP32 grouped GEMM)
+ *     t10_ggemm             per-sector torch.matmul loop              UniTensor.py:3727-3741
+ *                           dense tensordot / Matmul GEMM             UniTensor.py:3769, linalg.py:722-733
+ *
+ * Conventions
+ *   - every function returns T10_OK (0) or an error code; t10_last_error() gives the text
+ *     (thread-local).  No exceptions cross the ABI.
+ *   - pointers prefixed d_ are DEVICE pointers, h_ are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - the library never owns user data; scratch needed while BUILDING maps is
+ *     stream-ordered (cudaMallocAsync) and freed before return.  Hot-path calls
+ *     (relayout / permute / ggemm) allocate nothing and do not synchronise.
+ *   - bond tags: +1 = BRA, -1 = KET (Bond.py:41).
+ */
+#ifndef TOR10_B200_H
+#define TOR10_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T10_ABI_VERSION 1
+#define T10_MAX_RANK 16          /* bonds per tensor                                   */
+#define T10_MAX_NSYM 8           /* symmetries per bond                                */
+#define T10_KEYSPACE_MAX (1ll << 26) /* product of per-symmetry total-charge ranges    */
+#define T10_ARENA_ALIGN 16       /* sector base alignment in ELEMENTS (128 B for f64)  */
+
+enum t10_status {
+  T10_OK = 0,
+  T10_ERR_INVALID = 1,     /* bad argument                                             */
+  T10_ERR_CUDA = 2,        /* a CUDA runtime call failed                               */
+  T10_ERR_KEYSPACE = 3,    /* total-charge key space exceeds T10_KEYSPACE_MAX          */
+  T10_ERR_NOBLOCK = 4,     /* row and column spaces share no sector (UniTensor.py:415) */
+  T10_ERR_UNSUPPORTED = 5  /* dtype / size outside what the kernels cover              */
+};
+
+enum t10_dtype { T10_F64 = 0, T10_F32 = 1 };
+enum t10_symkind { T10_SYM_U1 = 0, T10_SYM_ZN = 1 };
+
+typedef void* t10_stream_t;
+
+int t10_version(void);
+const char* t10_last_error(void);
+/* sm count, compute capability and opt-in shared memory of `device` */
+int t10_device_props(int device, int* sm_count, int* cc_major, int* cc_minor, int* smem_optin);
+
+/* ------------------------------------------------------------------ family 1 ---- */
+
+/* Total-charge table of a bond space: out[x, s] for x = row-major flat index over
+ * `nbonds` bonds.  Charges of bond b are first multiplied by signs[b] (+1/-1, no modular
+ * reduction: Bond.py:469-477), then folded left to right with U1: a+b, Zn: (a+b) mod n
+ * with the non-negative numpy remainder (Symmetry.py:33-34, :83-84).  A single bond is not
+ * passed through the rule.  h_qoff[b] = row offset of bond b inside d_qnums.            */
+int t10_fuse_qnums(int nbonds, int nsym, const int64_t* h_dims, const int32_t* h_signs,
+                   const int32_t* h_sym_kind, const int64_t* h_sym_n, const int64_t* h_qoff,
+                   const int64_t* d_qnums, int64_t* d_out, t10_stream_t stream);
+
+/* The block map of a symmetric tensor (bonds in MEMORY order, `rowrank` of them in row
+ * space).  R = prod dims[:rowrank], C = prod dims[rowrank:].
+ *   d_block_qnums [cap_sec, nsym]  sector charges, ascending lexicographic
+ *   d_ket_map     [R, 2]           (sector, offset) of every flat row, (-1,-1) if none
+ *   d_bra_map     [C, 2]           same for columns
+ *   d_ket_idx     [R]              flat rows grouped by sector, ascending inside a sector
+ *   d_bra_idx     [C]              same for columns
+ *   d_sec_info    [cap_sec, 8]     {rows, cols, ket_start, bra_start, arena_off, 0,0,0}
+ *   d_rowbase     [R]              arena element offset of the row's first element, -1 if none
+ *   d_coloff      [C]              column offset inside the sector, -1 if none
+ *   h_counts      [4]              {nsec, arena_elems (incl. alignment padding), n_ket_phys, n_bra_phys}
+ * cap_sec must be >= min(R, C).  Synchronises `stream` before returning.               */
+int t10_blockmap_build(int rank, int rowrank, int nsym, const int64_t* h_dims,
+                       const int32_t* h_braket, const int32_t* h_sym_kind,
+                       const int64_t* h_sym_n, const int64_t* h_qoff, const int64_t* d_qnums,
+                       int64_t cap_sec, int64_t* d_block_qnums, int64_t* d_ket_map,
+                       int64_t* d_bra_map, int64_t* d_ket_idx, int64_t* d_bra_idx,
+                       int64_t* d_sec_info, int64_t* d_rowbase, int32_t* d_coloff,
+                       int64_t* h_counts, t10_stream_t stream);
+
+/* out[t, p] = (idx[t] / strides[p]) mod-chain: multi-index of flat idx[t] for the given
+ * row-major strides (UniTensor.py:24-29).                                              */
+int t10_unravel(int64_t n, int nstrides, const int64_t* h_strides, const int64_t* d_idx,
+                int64_t* d_out, t10_stream_t stream);
+
+/* Relayout address tables for destination layout L read from source layout M.
+ * For t in [0,n): x = d_idx[t] is a flat index over `nb` bonds with dims h_dims; every
+ * digit i_p contributes i_p*h_srow[p] to the source flat row and i_p*h_scol[p] to the
+ * source flat column.  Writes d_to_row[t], d_to_col[t].                                */
+int t10_relayout_tables(int64_t n, int nb, const int64_t* h_dims, const int64_t* h_srow,
+                        const int64_t* h_scol, const int64_t* d_idx, int32_t* d_to_row,
+                        int32_t* d_to_col, t10_stream_t stream);
+
+/* ------------------------------------------------------------------ family 2 ---- */
+
+/* Block-sparse strided permute (gather form).  For every destination sector s, row r,
+ * column c:   dst[off_s + r*ld_s + c] = src[rowbase[RR[ks+r]+CR[bs+c]] + coloff[RC[ks+r]+CC[bs+c]]]
+ * (0 where the source element is not stored).  d_tiles [ntiles,4] = {sector, r0, c0, 0};
+ * d_dst_sec [nsec,8] = {rows, cols, ket_start, bra_start, dst_off, dst_ld, 0, 0}.
+ * A tile covers T10_RELAYOUT_TR rows x T10_RELAYOUT_TC columns.
+ * d_src_ket_map / d_src_bra_map (the source layout's [R,2] / [C,2] maps) may be NULL; when
+ * given, an element is copied only if its source row and column lie in the SAME sector
+ * (needed for Zn layouts whose sign-flipped single-bond spaces lose sectors, quirk Q3).   */
+#define T10_RELAYOUT_TR 32
+#define T10_RELAYOUT_TC 128
+int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntiles,
+                        const int32_t* d_tiles, const int64_t* d_dst_sec,
+                        const int32_t* d_RR, const int32_t* d_RC, const int32_t* d_CR,
+                        const int32_t* d_CC, const int64_t* d_rowbase, const int32_t* d_coloff,
+                        const int64_t* d_src_ket_map, const int64_t* d_src_bra_map,
+                        t10_stream_t stream);
+
+/* Dense strided permute: dst (contiguous, shape = h_shape) [i0..i_{r-1}] =
+ * src[sum_k i_k * h_src_strides[k]]  (strides in elements).                            */
+int t10_permute_dense(int dtype, const void* d_src, void* d_dst, int rank,
+                      const int64_t* h_shape, const int64_t* h_src_strides, t10_stream_t stream);
+
+/* out[r, c] = a[r, c] * diag[c] (side = 1, column scaling) or diag[r] * a[r, c] (side = 0). */
+int t10_diag_scale(int dtype, const void* d_a, const void* d_diag, void* d_out, int64_t rows,
+                   int64_t cols, int side, t10_stream_t stream);
+
+/* ------------------------------------------------------------------ family 3 ---- */
+
+/* One GEMM of a group: C[m,n] (row-major, ldc) = A[m,k] (row-major, lda) * B[k,n]
+ * (row-major, ldb); offsets in ELEMENTS from the operand base pointers.                */
+typedef struct t10_gemm_problem {
+  int64_t a_off, b_off, c_off;
+  int32_t m, n, k;
+  int32_t lda, ldb, ldc;
+} t10_gemm_problem;
+
+/* Tile decomposition used by t10_ggemm for `tile_cfg` (0: 64x64, 1: 128x128, 2: 128x64).
+ * Fills h_tiles [cap,4] = {problem, m0, n0, 0} in launch order (heaviest first) and
+ * returns the tile count through *ntiles (call with h_tiles = NULL to size).           */
+int t10_ggemm_tile_shape(int tile_cfg, int* bm, int* bn);
+int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_problem* h_prob,
+                         int64_t cap, int32_t* h_tiles, int64_t* ntiles);
+
+/* Grouped GEMM over the matched sectors: one persistent launch.                        */
+int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d_C,
+              int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
+              const int32_t* d_tiles, t10_stream_t stream);
+
+/* Peak-rate probes used by bench.py for the roofline denominators (register-resident
+ * DMMA / DFMA loops; returns achieved TFLOP/s through *tflops).                        */
+int t10_probe_f64_peak(int use_dmma, int iters, double* tflops, t10_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOR10_B200_H */

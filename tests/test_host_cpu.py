@@ -1,0 +1,230 @@
+"""CPU suite for the product's host side: the C-ABI library loads and exports every symbol the header
+declares (no compute call is made without a GPU), Bond / Symmetry / Network / label algebra behave as
+the reference's, the product refuses to compute without CUDA, and the N>1 sector gather works over gloo.
+"""
+import copy
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def T():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_t10_build", os.path.join(ROOT, "tor10_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_library()
+    import tor10_b200
+    return tor10_b200
+
+
+def test_abi_exports_every_declared_symbol(T):
+    hdr = open(os.path.join(ROOT, "include", "tor10_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(t10_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 13
+    lib = ctypes.CDLL(T._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(T._lib.SIGNATURES), declared ^ set(T._lib.SIGNATURES)
+    assert T._lib.load().t10_version() == 1
+    assert ctypes.sizeof(T._lib.GemmProblem) == 48
+
+
+def test_tile_planner_host_side(T):
+    """t10_ggemm_plan_tiles is host code: heaviest tiles first, every output element covered once."""
+    prob = np.zeros(3, dtype=T._lib.GEMM_PROBLEM_DTYPE)
+    prob[0] = (0, 0, 0, 130, 70, 40, 40, 70, 70)
+    prob[1] = (0, 0, 0, 5, 5, 500, 500, 5, 5)
+    prob[2] = (0, 0, 0, 0, 9, 9, 9, 9, 9)
+    for cfg, (bm, bn) in {0: (64, 64), 1: (128, 128), 2: (128, 64)}.items():
+        n = ctypes.c_int64(0)
+        lib = T._lib.load()
+        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), 0, None, ctypes.byref(n)) == 0
+        tiles = np.zeros((n.value, 4), dtype=np.int32)
+        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), n.value, T._lib.np_ptr(tiles), ctypes.byref(n)) == 0
+        want = -(-130 // bm) * -(-70 // bn) + 1
+        assert n.value == want
+        assert tiles[0, 0] == 1                     # k=500 problem first
+        assert set(tiles[:, 0].tolist()) == {0, 1}  # empty problem produces no tile
+        b0, b1 = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.t10_ggemm_tile_shape(cfg, ctypes.byref(b0), ctypes.byref(b1)) == 0 and (b0.value, b1.value) == (bm, bn)
+
+
+def test_no_cpu_compute_path(T):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    b1 = T.Bond(2, T.BD_KET, qnums=[[0], [1]])
+    b2 = T.Bond(2, T.BD_BRA, qnums=[[0], [1]])
+    with pytest.raises(RuntimeError):
+        T.UniTensor(bonds=[b1, b2], rowrank=1)                   # block map is a CUDA kernel
+    x = T.UniTensor(bonds=[T.Bond(2), T.Bond(3)], rowrank=1)
+    y = T.UniTensor(bonds=[T.Bond(3), T.Bond(2)], rowrank=1, labels=[1, 2])
+    with pytest.raises(RuntimeError):
+        T.Contract(x, y)
+    with pytest.raises(RuntimeError):
+        T.Matmul(x, y)
+
+
+def test_bond_matches_reference_goldens(T, golden):
+    z, specs = golden("bond")
+    for key, sp in specs.items():
+        syms = [T.Symmetry.U1() if s[0] == "U1" else T.Symmetry.Zn(s[1]) for s in sp["syms"]]
+        a = T.Bond(len(sp["raw_a"]), T.BD_KET, qnums=sp["raw_a"], sym_types=syms)
+        b = T.Bond(len(sp["raw_b"]), T.BD_KET, qnums=sp["raw_b"], sym_types=syms)
+        assert np.array_equal(a.qnums, z[key + "/a_sorted"]) and np.array_equal(b.qnums, z[key + "/b_sorted"])
+        assert np.array_equal(a.GetUniqueQnums(), z[key + "/a_unique"])
+        assert np.array_equal(T._fx_GetCommRows(a.GetUniqueQnums(), b.GetUniqueQnums()), z[key + "/comm"])
+        c = copy.deepcopy(a)
+        c.combine(b)
+        assert c.dim == a.dim * b.dim and np.array_equal(c.qnums, z[key + "/combined"])
+        assert a.qnums is copy.deepcopy(a).qnums             # copies share the immutable table
+        assert a.signature() == copy.deepcopy(a).signature()
+        assert (c.signature() == a.signature()) == (c.dim == a.dim and np.array_equal(c.qnums, a.qnums))
+
+
+def test_bond_api_errors_and_docstring_kats(T):
+    with pytest.raises(Exception):
+        T.Bond(0)
+    with pytest.raises(Exception):
+        T.Bond(2, T.BD_REG, qnums=[[0], [1]])                 # Bond.py:240-241
+    with pytest.raises(ValueError):
+        T.Bond(3, T.BD_KET, qnums=[[0], [1]])
+    with pytest.raises(TypeError):
+        T.Bond(2, T.BD_KET, qnums=[[0], [5]], sym_types=[T.Symmetry.Zn(3)])
+    with pytest.raises(ValueError):
+        T.Symmetry.Zn(1)
+    a = T.Bond(3, T.BD_BRA, qnums=[[0], [0], [1]])
+    b = T.Bond(4, T.BD_BRA, qnums=[[0], [2], [-3], [-1]])
+    assert a.qnums.flatten().tolist() == [1, 0, 0] and b.qnums.flatten().tolist() == [2, 0, -1, -3]
+    a.combine(b)                                               # Bond.py:341-347
+    assert a.qnums.flatten().tolist() == [3, 1, 0, -2, 2, 0, -1, -3, 2, 0, -1, -3]
+    z1 = T.Bond(3, T.BD_BRA, qnums=[[0], [2], [1]], sym_types=[T.Symmetry.Zn(4)])
+    z1 * -1                                                    # in-place flip, no mod (Bond.py:469-477)
+    assert z1.qnums.flatten().tolist() == [-2, -1, 0]
+    assert z1.GetDegeneracy(-1) == 1
+    assert (T.Bond(3) == T.Bond(3)) and not (T.Bond(3) == T.Bond(4))
+    with pytest.raises(ValueError):
+        _ = T.Bond(3) == 3
+    with pytest.raises(ValueError):
+        a.qnums[0, 0] = 7                                      # immutable: keeps plan-cache keys honest
+
+
+def test_dense_metadata_matches_reference_tests(T):
+    """tests/test_UniTensor.py:10-81 of the reference (labels, Reshape, Permute) -- metadata only."""
+    cpu = torch.device("cpu")
+    os.environ["TOR10_B200_FORCE_CUDA"] = "0"
+    try:
+        ut = T.UniTensor(bonds=[T.Bond(3), T.Bond(4), T.Bond(5)], rowrank=2, labels=[10, 11, 12], device=cpu)
+        ut.SetLabel(2, 1)
+        assert ut.labels.tolist() == [10, 2, 12]
+        ut.SetLabels([3, 4, 5])
+        assert ut.labels.tolist() == [3, 4, 5]
+        with pytest.raises(ValueError):
+            ut.SetLabels([1, 1, 2])
+        r = ut.Reshape([12, 5], rowrank=1)
+        assert tuple(r.shape) == (12, 5) and r.rowrank == 1 and r.labels.tolist() == [0, 1]
+        ut.Permute([2, 0, 1], rowrank=1)
+        assert tuple(ut.shape) == (5, 3, 4) and ut.labels.tolist() == [5, 3, 4] and ut.rowrank == 1
+        assert not ut.is_contiguous()
+        ut.Permute([3, 4, 5], by_label=True)
+        assert tuple(ut.shape) == (3, 4, 5)
+        with pytest.raises(Exception):
+            T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], labels=[1, 1], rowrank=1, device=cpu)
+        with pytest.raises(Exception):
+            T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], device=cpu)          # rowrank required for untagged
+        d = T.UniTensor(bonds=[T.Bond(3), T.Bond(3)], rowrank=1, is_diag=True, device=cpu)
+        assert tuple(d.shape) == (3, 3) and d.Storage.shape == (3,)
+        tg = T.UniTensor(bonds=[T.Bond(2, T.BD_KET), T.Bond(2, T.BD_BRA)], device=cpu)
+        assert tg.rowrank == 1 and tg.is_braket_form()
+    finally:
+        os.environ.pop("TOR10_B200_FORCE_CUDA", None)
+
+
+def test_network_parser_and_checks(T, golden):
+    z, specs = golden("dense")
+    N = T.Network()
+    N.Fromstring(specs["net0"]["text"])
+    assert list(N.tensors) == ["A", "B", "C"] and N.Order == "(A,B),C"
+    assert N.TOUT[0].tolist() == [-1, -2] and N.TOUT[1].tolist() == [3, 4]
+    with pytest.raises(Exception):
+        N.Launch()                                             # nothing put (Network.py:397-398)
+    with pytest.raises(ValueError):
+        N.Put("Q", T.UniTensor(bonds=[T.Bond(2), T.Bond(2)], rowrank=1))
+    with pytest.raises(TypeError):
+        N.Put("B", T.UniTensor(bonds=[T.Bond(2), T.Bond(2), T.Bond(2)], rowrank=1))
+    for bad in ("A: 1 2; 3\n", "A 1;2\nTOUT: 1;2\n", "A: 1;2\nA: 2;3\nTOUT: 1;3\n", "A: 1;2\nTOUT: ;\nOrder: ((A)\n"):
+        with pytest.raises(Exception):
+            T.Network().Fromstring(bad)
+
+
+def test_label_match_is_label_sorted(T):
+    same, ai, bi, af, bf = T._plan.label_match(np.array([5, 30, 7, 21]), np.array([21, 9, 30]))
+    assert same.tolist() == [21, 30] and ai.tolist() == [3, 1] and bi.tolist() == [0, 2]   # quirk Q5
+    assert af.tolist() == [0, 2] and bf.tolist() == [1]
+
+
+def test_partition_contiguous(T):
+    from tor10_b200.parallel import partition_contiguous
+    cost = np.array([1, 1, 8, 1, 1, 1, 9, 1, 1], dtype=float)
+    b = partition_contiguous(cost, 3)
+    assert b[0] == 0 and b[-1] == len(cost) and len(b) == 4 and all(x <= y for x, y in zip(b, b[1:]))
+    assert max(cost[b[i]:b[i + 1]].sum() for i in range(3)) <= 11.0
+    assert partition_contiguous(np.ones(2), 4) == [0, 1, 2, 2, 2]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tor10_b200 import parallel
+    parallel.enable()
+    assert parallel.current_shard() == (rank, world)
+
+    class L:   # the three layout fields the gather needs
+        arena_off = np.array([0, 16, 48, 64])
+        arena_elems, nsec = 96, 4
+
+    bounds = parallel.partition_contiguous(np.array([3.0, 1.0, 1.0, 3.0]), world)
+    ranges = parallel.arena_ranges(L, bounds)
+    arena = torch.zeros(96 + 16, dtype=torch.float64)
+    lo, hi = ranges[rank]
+    arena[lo:hi] = rank + 1.0                      # "my sectors"
+    parallel.gather_ranges(arena, ranges, rank)
+    want = torch.zeros_like(arena)
+    for r, (lo, hi) in enumerate(ranges):
+        want[lo:hi] = r + 1.0
+    q.put((rank, bool(torch.equal(arena, want)), bounds))
+    dist.destroy_process_group()
+
+
+def test_sector_gather_world2_gloo(T):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == res[1][2] == [0, 2, 4]

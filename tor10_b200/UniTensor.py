@@ -1,0 +1,1236 @@
+"""UniTensor (API of tor10/UniTensor.py) on the B200 kernels.
+
+Same constructor, attributes, labels/bonds/rowrank semantics, mutation rules and error behaviour
+as the reference class (UniTensor.py:32-445).  What differs underneath:
+
+  * a symmetric tensor stores all its blocks in ONE device arena (sector bases aligned to 128 B);
+    `Storage` is a list of 2-D views into it, index-aligned with `_block_qnums`, so user code
+    that reads or assigns `T.Storage[b]` keeps working (assigned foreign tensors are packed back
+    into the arena before the next kernel launch);
+  * the block map (`_block_qnums`, `_Ket_mapper_blks`, ...) lives on the device inside a cached
+    `BlockLayout` and is built by the family-1 kernel; the numpy attributes of the reference are
+    materialised lazily from it;
+  * `Contiguous()` / `GetBlock` (non-contiguous) run the family-2 relayout kernel, `Contract` runs
+    relayout + one grouped-GEMM launch from a cached `ContractPlan`.
+
+There is no CPU compute path: symmetric tensors and every contraction need a CUDA device.
+"""
+import copy
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import _lib, _plan
+from .Bond import BD_BRA, BD_KET, BD_REG, Bond, BondType, _fx_GetCommRows
+
+DEBUG = False
+
+
+def _resolve_device(device):
+    """Scripts written for the reference pass torch.device("cpu") (e.g. iTEBD.py:26).  With a CUDA device
+    present and TOR10_B200_FORCE_CUDA unset or "1", tensors are placed on the GPU: the CPU path is the
+    reference, not this package."""
+    device = torch.device(device)
+    if device.type == "cpu" and torch.cuda.is_available() and os.environ.get("TOR10_B200_FORCE_CUDA", "1") == "1":
+        return torch.device("cuda", torch.cuda.current_device())
+    if device.type == "cuda" and device.index is None and torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _fx_decompress_idx(x, accu_offsets):
+    """UniTensor.py:24-29"""
+    y = []
+    for i in range(len(accu_offsets)):
+        y.append(np.array(x / accu_offsets[i]).astype(np.int64))
+        x = x % accu_offsets[i]
+    return np.array(y).swapaxes(0, 1)
+
+
+class _BlockList(list):
+    """`Storage` of a symmetric tensor.  Remembers whether an entry was replaced by the user."""
+    dirty = False
+
+    def __setitem__(self, k, v):
+        self.dirty = True
+        super().__setitem__(k, v)
+
+
+class UniTensor:
+
+    def _mac(self, torch_tensor=None, braket=None, sym_mappers=None):
+        """UniTensor.py:34-74.  `sym_mappers` here is (layout, arena, _mapper) -- the device-side
+        equivalent of the reference's 10-tuple of numpy maps."""
+        if braket is not None:
+            self.braket = copy.deepcopy(braket)
+            self._check_braket()
+        if sym_mappers is not None:
+            self._layout, self._arena, mapper = sym_mappers
+            self._set_mapper(mapper)
+            self._blocks = None
+            self._block_qnums = None
+        if torch_tensor is not None:
+            self.Storage = torch_tensor
+
+    def __init__(self, bonds, rowrank=None, labels=None, device=torch.device("cpu"), dtype=torch.float64,
+                 is_diag=False, requires_grad=False, name="", check=True):
+        self.name = name
+        self.bonds = np.array([copy.copy(bonds[i]) for i in range(len(bonds))], dtype=object)
+        if labels is None:
+            self.labels = np.arange(len(self.bonds)).astype(np.int64)
+        else:
+            self.labels = np.array(copy.deepcopy(labels), dtype=np.int64)
+        self._dense = None
+        self._arena = None
+        self._blocks = None
+        self._layout = None
+        self._mapper = None
+        self._inv_mapper = None
+        self._contiguous = True
+        self._block_qnums = None
+
+        if check:
+            if not len(self.labels) == (len(self.bonds)):
+                raise Exception("UniTensor.__init__", "labels size is not consistence with the rank")
+            if rowrank is not None:
+                if rowrank < 0 or rowrank > len(self.bonds):
+                    raise Exception("UniTensor.__init__", "the rowrank should be >=0 and < # of bonds")
+            if len(self.bonds) != 0:
+                if not len(np.unique(self.labels)) == len(self.labels):
+                    raise Exception("UniTensor.__init__", "labels contain duplicate element.")
+                isSymm = np.unique([(bd.qnums is None) for bd in self.bonds])
+                if len(isSymm) != 1:
+                    raise TypeError("UniTensor.__init__",
+                                    "the bonds are not consistent. Cannot have mixing bonds of with and without "
+                                    "symmetry (qnums).")
+            else:
+                if is_diag:
+                    raise Exception("UniTensor.__init__", "the scalar tensor (rank-0) cannot have is_diag=True.")
+
+        self.is_braket = None
+        self.braket = None
+        self.rowrank = rowrank
+
+        if check:
+            if len(self.bonds) != 0 and self.bonds[0].bondType != BD_REG:
+                self.braket = np.array([BondType[b.bondType] for b in self.bonds], dtype=np.int64)
+            if self.rowrank is None:
+                if len(self.bonds) == 0:
+                    self.rowrank = 0
+                elif self.braket is not None:
+                    self.rowrank = int((self.braket == BondType[BD_KET]).sum())
+                else:
+                    raise Exception("[ERROR] for UniTensor init with all the bond are regular, rowrank should be "
+                                    "provided")
+            else:
+                self.rowrank = int(rowrank)
+            self._check_braket()
+
+        self.is_symm = False if len(self.bonds) == 0 else (self.bonds[0].qnums is not None)
+        self.is_diag = is_diag
+
+        if not self.is_symm:
+            if check:
+                device = _resolve_device(device)
+                if is_diag:
+                    if not len(self.labels) == 2:
+                        raise TypeError("UniTensor.__init__", "is_diag=True require Tensor rank==2")
+                    if not self.rowrank == 1:
+                        raise TypeError("UniTensor.__init__",
+                                        "is_diag=True require Tensor rank==2, with 1 inbond and 1 outbond (rowrank=1)")
+                    if not self.bonds[0].dim == self.bonds[1].dim:
+                        raise TypeError("UniTensor.__init__", "is_diag=True require Tensor to be square rank-2")
+                    self._dense = torch.zeros(self.bonds[0].dim, device=device, dtype=dtype)
+                elif len(self.bonds) != 0:
+                    self._dense = torch.zeros(tuple(int(b.dim) for b in self.bonds), device=device, dtype=dtype)
+                else:
+                    self._dense = torch.tensor(0, device=device, dtype=dtype)
+        else:
+            if check:
+                if len(np.unique([bd.nsym for bd in self.bonds])) != 1:
+                    raise TypeError("UniTensor.__init__", "the number of symmetry type for symmetry bonds doesn't match.")
+                if self.rowrank < 1 or self.rowrank >= len(self.bonds):
+                    raise TypeError("UniTensor.__init__",
+                                    "[ERROR] tensor with symmetry must have at least one rank for row space and one "
+                                    "rank for column space")
+                nbra = int((self.braket == BondType[BD_BRA]).sum())
+                if nbra < 1 or nbra >= len(self.bonds):
+                    raise TypeError("UniTensor.__init__",
+                                    "[ERROR] tensor with symmetry must have at least one bra-bond and one ket-bond")
+                _lib.dtype_code(dtype)
+                device = _lib.require_cuda(_resolve_device(device))
+                # block map: family-1 kernel, cached per signature (UniTensor.py:393-441)
+                self._layout = _plan.get_layout(list(self.bonds), self.braket, self.rowrank, device)
+                self._arena = self._layout.new_arena(dtype, zero=True)
+                self._set_mapper(np.arange(len(self.bonds), dtype=np.int64))
+
+        if check and requires_grad:
+            self.requires_grad(True)
+
+    # ------------------------------------------------------------------ internals ----
+    @classmethod
+    def _from_plan(cls, bonds, labels, braket, rowrank, layout, arena, name=""):
+        """Symmetric tensor from an already-built layout + arena (result of Contract / Contiguous)."""
+        t = cls.__new__(cls)
+        t.name = name
+        t.bonds = np.array([copy.copy(b) for b in bonds], dtype=object)
+        t.labels = np.array(labels, dtype=np.int64)
+        t.braket = np.array(braket, dtype=np.int64)
+        t.rowrank = int(rowrank)
+        t.is_symm, t.is_diag = True, False
+        t._dense, t._blocks, t._block_qnums = None, None, None
+        t._layout, t._arena = layout, arena
+        t._set_mapper(np.arange(len(bonds), dtype=np.int64))
+        t.is_braket = None
+        t._check_braket()
+        return t
+
+    def _set_mapper(self, mapper):
+        self._mapper = np.array(mapper, dtype=np.int64)
+        rng = np.arange(len(self._mapper), dtype=np.int64)
+        self._contiguous = bool((self._mapper == rng).all())            # UniTensor.py:2300-2304 (quirk Q1)
+        self._inv_mapper = np.zeros(len(self._mapper), dtype=np.int64)
+        self._inv_mapper[self._mapper] = rng
+
+    def _logical_layout(self):
+        return _plan.get_layout(list(self.bonds), self.braket, self.rowrank, self._arena.device)
+
+    def _arena_tensor(self):
+        """The arena with any user-assigned blocks packed back in."""
+        bl = self._blocks
+        if bl is not None and bl.dirty:
+            views = self._layout.views(self._arena)
+            if len(bl) != len(views):
+                raise RuntimeError("UniTensor.Storage: number of blocks changed")
+            for b, v in enumerate(views):
+                x = bl[b]
+                if x.data_ptr() == v.data_ptr() and x.shape == v.shape and x.is_contiguous():
+                    continue
+                if tuple(x.shape) != tuple(v.shape):
+                    raise RuntimeError("UniTensor.Storage[%d]: block of shape %s assigned where %s is required"
+                                       % (b, tuple(x.shape), tuple(v.shape)))
+                v.copy_(x)
+                list.__setitem__(bl, b, v)
+            bl.dirty = False
+        return self._arena
+
+    @property
+    def Storage(self):
+        if self.is_symm:
+            if self._blocks is None:
+                self._blocks = _BlockList(self._layout.views(self._arena))
+            return self._blocks
+        return self._dense
+
+    @Storage.setter
+    def Storage(self, value):
+        if getattr(self, "is_symm", False):
+            bl = _BlockList(value)
+            bl.dirty = True
+            self._blocks = bl
+        else:
+            self._dense = value
+
+    # reference attribute names, materialised from the device maps on demand
+    @property
+    def _Ket_mapper_blks(self):
+        return self._layout.host("ket_map")
+
+    @property
+    def _Bra_mapper_blks(self):
+        return self._layout.host("bra_map")
+
+    @property
+    def _Ket_invmapper_blks(self):
+        return self._layout.host("ket_inv")
+
+    @property
+    def _Bra_invmapper_blks(self):
+        return self._layout.host("bra_inv")
+
+    @property
+    def _accu_off_in(self):
+        return self._layout.accu_in
+
+    @property
+    def _accu_off_out(self):
+        return self._layout.accu_out
+
+    @property
+    def _block_qnums(self):
+        if not self.is_symm:
+            return None
+        if self._bq is None:
+            lay = self._layout if self._contiguous and self.rowrank == self._layout.rowrank else self._logical_layout()
+            self._bq = lay.block_qnums
+        return self._bq
+
+    @_block_qnums.setter
+    def _block_qnums(self, v):
+        self._bq = v
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        if self.is_symm:
+            d["_pickled_blocks"] = [x.detach().cpu() for x in self.Storage]
+            d["_pickled_device"] = str(self._arena.device)
+            for k in ("_arena", "_blocks", "_layout", "_bq"):
+                d.pop(k, None)
+        return d
+
+    def __setstate__(self, d):
+        blocks = d.pop("_pickled_blocks", None)
+        dev = d.pop("_pickled_device", None)
+        self.__dict__.update(d)
+        if blocks is not None:
+            device = _lib.require_cuda(_resolve_device(dev))
+            # memory layout = bonds in memory order
+            mem_bonds = [self.bonds[self._inv_mapper[i]] for i in range(len(self.bonds))]
+            mem_braket = self.braket[self._inv_mapper]
+            rr = d.get("_mem_rowrank", self.rowrank)
+            self._layout = _plan.get_layout(mem_bonds, mem_braket, rr, device)
+            self._arena = self._layout.new_arena(blocks[0].dtype, zero=True)
+            self._blocks, self._bq = None, None
+            for v, x in zip(self._layout.views(self._arena), blocks):
+                v.copy_(x)
+
+    # ------------------------------------------------------------------ tags ---------
+    def tag_braket(self, tags=None):
+        if self.braket is None:
+            if tags is None:
+                self.braket = []
+                for b_in in range(self.rowrank):
+                    self.bonds[b_in].change(BD_KET)
+                    self.braket.append(BondType[BD_KET])
+                for b_out in range(len(self.bonds) - self.rowrank):
+                    self.bonds[b_out + self.rowrank].change(BD_BRA)
+                    self.braket.append(BondType[BD_BRA])
+            else:
+                if len(tags) != len(self.bonds):
+                    raise ValueError("[ERROR] tags must match the rank of bonds.")
+                if any([x is BD_REG for x in tags]):
+                    raise ValueError("[ERROR] tags cannot contain BD_REG")
+                self.braket = []
+                for b in range(len(self.bonds)):
+                    self.bonds[b].change(tags[b])
+                    self.braket.append(BondType[tags[b]])
+            self.braket = np.array(self.braket, dtype=np.int64)
+            self._check_braket()
+
+    def untag_braket(self):
+        if self.is_symm:
+            raise Exception("[ERROR]", "Cannot untag bra/ket on the bonds for symmetry tensor.")
+        if self.braket is None:
+            return
+        self.is_braket = None
+        self.braket = None
+        for b in range(len(self.bonds)):
+            self.bonds[b].change(BD_REG)
+
+    def _check_braket(self):
+        if self.braket is not None:
+            if (self.braket[:self.rowrank] == BondType[BD_KET]).all() and (
+                    self.braket[self.rowrank:] == BondType[BD_BRA]).all():
+                self.is_braket = True
+            else:
+                self.is_braket = False
+
+    def is_braket_form(self):
+        if self.braket is None:
+            raise Exception("[ERROR] for a tensor with regular bonds, there is no property of barket.")
+        return self.is_braket
+
+    def braket_form(self):
+        if self.braket is None:
+            raise Exception("[ERROR] for a tensor with regular bonds, there is no property of barket.")
+        x = np.argsort(self.braket, kind="stable")
+        Nin = int((self.braket == BondType[BD_KET]).sum())
+        self.Permute(x, rowrank=Nin, by_label=False)
+        return self
+
+    # ------------------------------------------------------------------ setters ------
+    def SetLabel(self, newLabel, idx):
+        if not type(newLabel) is int or not type(idx) is int:
+            raise TypeError("UniTensor.SetLabel", "newLabel and idx must be int.")
+        if not idx < len(self.labels):
+            raise ValueError("UniTensor.SetLabel", "idx exceed the number of bonds.")
+        if newLabel in self.labels:
+            raise ValueError("UniTensor.SetLabel", "newLabel [%d] already exists in the current UniTensor." % newLabel)
+        self.labels[idx] = newLabel
+
+    def SetLabels(self, newlabels):
+        if isinstance(newlabels, list):
+            newlabels = np.array(newlabels)
+        if not len(newlabels) == len(self.labels):
+            raise ValueError("UniTensor.SetLabels", "the length of newlabels does not match with the rank of UniTensor.")
+        if len(np.unique(newlabels)) != len(newlabels):
+            raise ValueError("UniTensor.SetLabels", "the newlabels contain duplicate entries.")
+        self.labels = np.array(newlabels, dtype=np.int64)
+
+    def SetName(self, name):
+        if not isinstance(name, str):
+            raise TypeError("UniTensor.str", "the name should be a string.")
+        self.name = name
+        return self
+
+    def SetElem(self, elem):
+        if not isinstance(elem, list) and not isinstance(elem, np.ndarray):
+            raise TypeError("UniTensor.SetElem", "[ERROR]  elem can only be python-list or numpy")
+        if self.is_symm:
+            raise Exception("UniTensor.SetElem", "[ERROR] the TN that has symm should use PutBlock.")
+        if not len(elem) == self._dense.numel():
+            raise ValueError("UniTensor.SetElem", "[ERROR] number of elem is not equal to the # of elem in the tensor.")
+        raw = np.array(elem)
+        if len(raw.shape) != 1:
+            raise Exception("UniTensor.SetElem", "[ERROR] can only accept 1D array of elements.")
+        st = self._dense
+        self._dense = torch.from_numpy(raw).type(st.dtype).reshape(st.shape).to(st.device)
+
+    def SetRowRank(self, new_rowrank):
+        if self.is_symm:
+            if new_rowrank < 1 or new_rowrank > len(self.labels) - 1:
+                raise Exception("[ERROR]", "SetRowRank for a tensor with symmetry must have at least 1 bond in "
+                                           "row-space and 1 bond in col-space")
+            self.rowrank = int(new_rowrank)
+            self._bq = None
+        else:
+            if new_rowrank < 0 or new_rowrank > len(self.labels):
+                raise Exception("[ERRROR]", "Invalid Rowrank. Must >=0 and <= rank of tensor for non-symmetry UniTensor")
+            self.rowrank = int(new_rowrank)
+        self._check_braket()
+        return self
+
+    def Todense_(self):
+        if self.is_symm:
+            raise Exception("UniTensor.Todense()", "[ERROR] cannot transform to dense for UniTensor with symmetry")
+        if self.is_diag:
+            self._dense = torch.diag(self._dense)
+            self.is_diag = False
+        return self
+
+    def Todense(self):
+        if self.is_symm:
+            raise Exception("UniTensor.Todense()", "[ERROR] cannot transform to dense form for symmetric UniTensor")
+        if self.is_diag:
+            out = copy.deepcopy(self)
+            out.Todense_()
+            return out
+        return self
+
+    def to_(self, device):
+        if not isinstance(device, torch.device):
+            raise TypeError("[ERROR] UniTensor.to()", "only support device argument in this version as torch.device")
+        device = _resolve_device(device)
+        if self.device != device:
+            if self.is_symm:
+                _lib.require_cuda(device)
+                arena = self._arena_tensor().to(device)
+                mem_bonds = [self.bonds[self._inv_mapper[i]] for i in range(len(self.bonds))]
+                self._layout = _plan.get_layout(mem_bonds, self.braket[self._inv_mapper], self._layout.rowrank, device)
+                self._arena, self._blocks = arena, None
+            else:
+                self._dense = self._dense.to(device)
+        return self
+
+    def to(self, device):
+        if not isinstance(device, torch.device):
+            raise TypeError("[ERROR] UniTensor.to()", "only support device argument in this version as torch.device")
+        if self.device != _resolve_device(device):
+            out = copy.deepcopy(self)
+            out.to_(device)
+            return out
+        return self
+
+    # ------------------------------------------------------------------ printing -----
+    def Print_diagram(self, bond_info=False):
+        print("-----------------------")
+        print("tensor Name : %s" % self.name)
+        print("tensor Rank : %d" % (len(self.labels)))
+        print("has_symmetry: %s" % ("True" if self.is_symm else "False"))
+        print("on device     : %s" % self.device)
+        if not self.is_symm:
+            print("is_diag       : %s" % ("True" if self.is_diag else "False"))
+        Nin, Nout = self.rowrank, len(self.bonds) - self.rowrank
+        vl = max(Nin, Nout)
+        tagged = self.braket is not None
+        if tagged:
+            print("braket_form : %s" % ("True" if self.is_braket else "False"))
+            print("      |ket>               <bra| ")
+            print("           ---------------      ")
+        else:
+            print("            -------------      ")
+        for i in range(vl):
+            print("           |             |     " if (tagged or i) else "           /             \\     ")
+            if i < Nin:
+                bks = "__" if not tagged else ("> " if self.braket[i] == BondType[BD_KET] else "<*")
+                l, llbl = "%3d %s__" % (self.labels[i], bks), "%-3d" % self.bonds[i].dim
+            else:
+                l, llbl = "        ", "   "
+            if i < Nout:
+                bks = "__" if not tagged else ("*>" if self.braket[Nin + i] == BondType[BD_KET] else " <")
+                r, rlbl = "__%s %-3d" % (bks, self.labels[Nin + i]), "%3d" % self.bonds[Nin + i].dim
+            else:
+                r, rlbl = "        ", "   "
+            print("   %s| %s     %s |%s" % (l, llbl, rlbl, r))
+        if tagged:
+            print("           |             |     ")
+            print("           ---------------     ")
+        else:
+            print("           \\             /     ")
+            print("            -------------      ")
+        if bond_info:
+            for i in range(len(self.bonds)):
+                print("lbl:%d " % (self.labels[i]), end="")
+                print(self.bonds[i])
+
+    def __str__(self):
+        print("Tensor name: %s" % self.name)
+        if self.braket is not None:
+            print("braket_form : %s" % ("True" if self.is_braket else "False"))
+        if self.is_symm:
+            print("[Symmetry]")
+            src = self if self._contiguous else self.Contiguous()
+            for b in range(len(src.Storage)):
+                print(src.Storage[b])
+        else:
+            print("is_diag    : %s" % ("True" if self.is_diag else "False"))
+            print(self._dense)
+        return ""
+
+    __repr__ = __str__
+
+    def __len__(self):
+        if self.is_symm:
+            raise Exception("[ERROR]", "UniTensor with symmetry doesn't have property len")
+        return len(self._dense)
+
+    def __eq__(self, rhs):
+        """Same structure (bonds, labels, braket, rowrank, kind) -- not values (UniTensor.py:1014-1056)."""
+        if not isinstance(rhs, self.__class__):
+            raise ValueError("Bond.__eq__", "[ERROR] invalid comparison between Bond object and other type class.")
+        if self.is_symm != rhs.is_symm or len(self.bonds) != len(rhs.bonds):
+            return False
+        if not (all(self.bonds[i] == rhs.bonds[i] for i in range(len(self.bonds))) and
+                all(self.labels[i] == rhs.labels[i] for i in range(len(self.labels)))):
+            return False
+        if self.rowrank != rhs.rowrank:
+            return False
+        if (self.braket is None) != (rhs.braket is None):
+            return False
+        if self.braket is not None and not (self.braket == rhs.braket).all():
+            return False
+        if self.is_symm:
+            return True
+        return (self.is_diag == rhs.is_diag) and (self._dense.shape == rhs._dense.shape)
+
+    def __ne__(self, other):
+        return not (self == other)
+
+    __hash__ = None
+
+    @property
+    def device(self):
+        return self._arena.device if self.is_symm else self._dense.device
+
+    @property
+    def dtype(self):
+        return self._arena.dtype if self.is_symm else self._dense.dtype
+
+    @property
+    def shape(self):
+        if self.is_symm:
+            return torch.Size([int(b.dim) for b in self.bonds])
+        if self.is_diag:
+            return torch.Size([int(self.bonds[0].dim), int(self.bonds[0].dim)])
+        return self._dense.shape
+
+    def __getitem__(self, key):
+        if self.is_symm:
+            raise Exception("UniTensor.__getitem__",
+                            "[ERROR] cannot use [] to getitem from a block-form tensor. Use get block first.")
+        return From_torch(self._dense[key], rowrank=0)
+
+    def __setitem__(self, key, value):
+        if self.is_symm:
+            raise Exception("UniTensor.__setitem__",
+                            "[ERROR] cannot use [] to setitem from a block-form tensor. Use get block first.")
+        self._dense[key] = value
+
+    def item(self):
+        if self.is_symm:
+            raise TypeError("UniTensor.item", "[ERROR] cannot operate item() on symmetry tensor")
+        if self._dense.numel() != 1:
+            raise TypeError("UniTensor.item", "[ERROR] only one-element tensors can be converted to Python scalars.")
+        return self._dense.item()
+
+    # ------------------------------------------------------------------ arithmetic ---
+    def _like(self, storage, is_diag=None):
+        if self.is_symm:
+            t = UniTensor._from_plan(self.bonds, self.labels, self.braket, self.rowrank, self._layout, storage,
+                                     name="")
+            t._set_mapper(self._mapper)
+            t._bq = self._bq
+            return t
+        t = UniTensor(bonds=self.bonds, labels=self.labels, rowrank=self.rowrank, check=False,
+                      is_diag=self.is_diag if is_diag is None else is_diag)
+        t._mac(torch_tensor=storage, braket=self.braket)
+        return t
+
+    def _binary(self, other, op, name, reverse=False):
+        f = (lambda x, y: op(y, x)) if reverse else op
+        if isinstance(other, self.__class__):
+            if self.is_symm != other.is_symm:
+                raise TypeError("[ERROR]", "Cannot %s two symm and non-symm UniTensor " % name)
+            if self.is_symm:
+                if self != other:
+                    raise TypeError("[ERROR]", "Cannot %s two symm tensors that have different symmetry structure." % name)
+                if not (self.is_contiguous() and other.is_contiguous()):
+                    raise Exception("[ERROR]", "Two symmetry tensors can only %s when both are contiguous.\n suggestion: "
+                                               "Call .Contiguous() or .Contiguous_() before %s" % (name, name))
+                return self._like(f(self._arena_tensor(), other._arena_tensor()))
+            if (self.braket is None) != (other.braket is None):
+                raise Exception("[ERROR]", "Cannot %s non-braket-tag tensor with tagged tensor" % name)
+            if self.is_diag and other.is_diag:
+                return self._like(f(self._dense, other._dense), is_diag=True)
+            if self.is_diag:
+                return self._like(f(torch.diag(self._dense), other._dense), is_diag=False)
+            if other.is_diag:
+                return self._like(f(self._dense, torch.diag(other._dense)), is_diag=False)
+            return self._like(f(self._dense, other._dense), is_diag=False)
+        if self.is_symm:
+            return self._like(f(self._arena_tensor(), other))
+        return self._like(f(self._dense, other))
+
+    def __add__(self, other):
+        return self._binary(other, torch.add, "+")
+
+    def __radd__(self, other):
+        return self._binary(other, torch.add, "+", reverse=True)
+
+    def __sub__(self, other):
+        return self._binary(other, torch.sub, "-")
+
+    def __rsub__(self, other):
+        return self._binary(other, lambda x, y: x - y, "-", reverse=True)
+
+    def __mul__(self, other):
+        return self._binary(other, torch.mul, "*")
+
+    def __rmul__(self, other):
+        return self._binary(other, torch.mul, "*", reverse=True)
+
+    def __truediv__(self, other):
+        return self._binary(other, torch.div, "/")
+
+    def __pow__(self, other):
+        if self.is_symm:
+            return self._like(self._arena_tensor() ** other)
+        return self._like(self._dense ** other)
+
+    def _inplace(self, other, op, name):
+        res = self._binary(other, op, name)
+        if self.is_symm:
+            self._arena, self._blocks = res._arena, None
+        else:
+            self._dense, self.is_diag = res._dense, res.is_diag
+        return self
+
+    def __iadd__(self, other):
+        return self._inplace(other, torch.add, "+")
+
+    def __isub__(self, other):
+        return self._inplace(other, torch.sub, "-")
+
+    def __imul__(self, other):
+        return self._inplace(other, torch.mul, "*")
+
+    def Whole_transpose(self):
+        """Swap row and column spaces (UniTensor.py:1386-1425)."""
+        n = len(self.bonds)
+        self.Permute(list(range(self.rowrank, n)) + list(range(self.rowrank)), rowrank=n - self.rowrank)
+        return self
+
+    # ------------------------------------------------------------------ linalg wrappers
+    def Svd(self):
+        if self.is_symm:
+            raise Exception("UniTensor.Svd", "[ERROR] cannot perform Svd on a symmetry,block-form tensor. use GetBlock() "
+                                             "first and perform svd on the Block.")
+        from . import linalg
+        return linalg.Svd(self)
+
+    def Svd_truncate(self, keepdim=None):
+        if self.is_symm:
+            raise Exception("UniTensor.Svd_truncate", "[ERROR] cannot perform Svd on a symmetry,block-form tensor. use "
+                                                      "GetBlock() first and perform svd on the Block.")
+        from . import linalg
+        return linalg.Svd_truncate(self, keepdim)
+
+    def Norm(self):
+        from . import linalg
+        return linalg.Norm(self)
+
+    def Det(self):
+        from . import linalg
+        return linalg.Det(self)
+
+    def Matmul(self, b):
+        if self.is_symm:
+            raise Exception("UniTensor.Matmul", "[ERROR] cannot perform MatMul on a symmetry,block-form tensor. use "
+                                                "GetBlock() first and perform matmul on the Block.")
+        from . import linalg
+        return linalg.Matmul(self, b)
+
+    def Rand(self):
+        _Randomize(self)
+        return self
+
+    def CombineBonds(self, X_to_combine, new_label=None, permute_back=False, by_label=True):
+        if len(X_to_combine) < 2:
+            raise ValueError("CombineBonds", "[ERROR] the number of bonds to combine should be greater than one.")
+        if by_label:
+            lbl = {int(l): i for i, l in enumerate(self.labels)}
+            if not all(int(x) in lbl for x in X_to_combine):
+                raise Exception("UniTensor.CombineBonds", "[ERROR] label_to_combine doesn't exists in the UniTensor")
+            idxs = np.array([lbl[int(x)] for x in X_to_combine])
+        else:
+            if not all(x < len(self.labels) for x in X_to_combine):
+                raise Exception("UniTensor.CombineBonds", "[ERROR] index_to_combine doesn't exists in the UniTensor")
+            idxs = np.array(X_to_combine)
+        _CombineBonds(self, idxs, new_label, permute_back)
+
+    # ------------------------------------------------------------------ relayout -----
+    def Contiguous_(self):
+        """UniTensor.py:2016-2059"""
+        if self.is_symm:
+            if self._contiguous:
+                return self
+            out = self.Contiguous()
+            out.name = self.name
+            self.__dict__.update(out.__dict__)
+            return self
+        self._dense = self._contiguous_dense(self._dense)
+        return self
+
+    def Contiguous(self):
+        """UniTensor.py:2061-2145.  Symmetric: one launch of the family-2 block relayout kernel (the
+        reference runs a Python loop over every stored element, :2108-2129)."""
+        if self.is_symm:
+            if self._contiguous:
+                return self
+            L = self._logical_layout()
+            plan = _plan.get_relayout(self._layout, L, self._mapper, padded=False)
+            src = self._arena_tensor()
+            with torch.cuda.device(src.device):
+                dst = L.new_arena(src.dtype, zero=False)
+                plan.run(src, dst)
+            return UniTensor._from_plan(self.bonds, self.labels, self.braket, self.rowrank, L, dst, name="")
+        if self._dense.is_contiguous():
+            return self
+        tmp = UniTensor(bonds=self.bonds, labels=self.labels, rowrank=self.rowrank, check=False)
+        tmp._mac(braket=self.braket, torch_tensor=self._contiguous_dense(self._dense))
+        return tmp
+
+    @staticmethod
+    def _contiguous_dense(x):
+        """Tensor.contiguous() through the family-2 dense permute kernel."""
+        if x.is_contiguous():
+            return x
+        _lib.require_cuda_tensor(x, "dense relayout")
+        out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().t10_permute_dense(
+                _lib.dtype_code(x.dtype), x.data_ptr(), out.data_ptr(), x.dim(), _lib.np_ptr(_lib.i64(list(x.shape))),
+                _lib.np_ptr(_lib.i64(list(x.stride()))), _lib.stream_ptr()))
+        return out
+
+    def is_contiguous(self):
+        if self.is_symm:
+            return self._contiguous
+        return self._dense.is_contiguous()
+
+    def Permute(self, mapper, rowrank=None, by_label=False):
+        """UniTensor.py:2160-2327: metadata only."""
+        if not (isinstance(mapper, list) or isinstance(mapper, np.ndarray)):
+            raise TypeError("UniTensor.Permute", "[ERROR] mapper should be an 1d python list or numpy array.")
+        if len(mapper) != len(self.bonds):
+            raise ValueError("UniTensor.Permute", "[ERROR] len(mapper) should equal to Tensor rank")
+        if len(mapper) != len(np.unique(mapper)):
+            raise ValueError("UniTensor.Permute", "[ERROR] mapper contain duplicate elements.")
+        if by_label:
+            DD = dict(zip(self.labels.tolist(), range(len(self.labels))))
+            if not all(int(lbl) in DD for lbl in mapper):
+                raise Exception("UniTensor.Permute", "[ERROR] by_label=True but mapper contain invalid labels not appear "
+                                                     "in the UniTensor label")
+            idx_mapper = np.array([DD[int(x)] for x in mapper], dtype=np.int64)
+        else:
+            idx_mapper = np.array(mapper).astype(np.int64)
+        self.labels = self.labels[idx_mapper]
+        self.bonds = self.bonds[idx_mapper]
+        if self.braket is not None:
+            self.braket = self.braket[idx_mapper]
+        if rowrank is not None:
+            if rowrank < 0:
+                raise ValueError("UniTensor.Permute", "rowrank must >=0")
+            self.rowrank = int(rowrank)
+        self._check_braket()
+        if self.is_symm:
+            self._set_mapper(self._mapper[idx_mapper])
+            self._bq = None          # recomputed for the new split on demand (:2310-2313)
+        elif self.is_diag:
+            if self.rowrank != 1:
+                raise Exception("UniTensor.Permute", "[ERROR] UniTensor.is_diag=True must have rowrank==1\n" +
+                                "Suggest, call Todense()")
+        else:
+            self._dense = self._dense.permute(tuple(int(i) for i in idx_mapper))
+        return self
+
+    def _reshape_checks(self, dimer, what):
+        if self.is_symm:
+            raise TypeError("UniTensor.%s" % what, "[ERROR] Cannot perform %s on a symmetry Tensor" % what)
+        if self.is_diag:
+            raise Exception("UniTensor.%s" % what, "[ERROR] UniTensor.is_diag=True cannot be %s.\n" % what +
+                            "[Suggest] Call UniTensor.Todense()")
+        if self.braket is not None:
+            raise Exception("UniTensor.%s" % what, "[ERROR] UniTensor.%s can only operate on a [untagged] tensor with "
+                                                   "regular bonds (BD_REG)." % what)
+        if not isinstance(dimer, list):
+            raise TypeError("UniTensor.%s" % what, "[ERROR] mapper should be an python list.")
+
+    def Reshape(self, dimer, rowrank, new_labels=None):
+        self._reshape_checks(dimer, "Reshape")
+        x = self._contiguous_dense(self._dense)
+        new_Storage = (x.clone() if x is self._dense else x).reshape(dimer)
+        if new_labels is None:
+            new_labels = np.arange(len(dimer))
+        tmp = UniTensor(bonds=np.array([Bond(dimer[i]) for i in range(len(dimer))]), labels=new_labels,
+                        rowrank=rowrank, check=False)
+        tmp._mac(torch_tensor=new_Storage)
+        return tmp
+
+    def Reshape_(self, dimer, rowrank, new_labels=None):
+        self._reshape_checks(dimer, "Reshape")
+        self._dense = self._contiguous_dense(self._dense).reshape(dimer)
+        if new_labels is None:
+            new_labels = np.arange(len(dimer))
+        self.labels = np.array(new_labels, dtype=np.int64)
+        self.bonds = np.array([Bond(dimer[i]) for i in range(len(dimer))], dtype=object)
+        self.rowrank = rowrank
+        return self
+
+    def View(self, dimer, rowrank, new_labels=None):
+        self._reshape_checks(dimer, "View")
+        new_Storage = self._dense.view(dimer)
+        if new_labels is None:
+            new_labels = np.arange(len(dimer))
+        tmp = UniTensor(bonds=np.array([Bond(dimer[i]) for i in range(len(dimer))]), labels=new_labels,
+                        rowrank=rowrank, check=False)
+        tmp._mac(torch_tensor=new_Storage)
+        return tmp
+
+    def View_(self, dimer, rowrank, new_labels=None):
+        self._reshape_checks(dimer, "View")
+        self._dense = self._dense.view(dimer)
+        if new_labels is None:
+            new_labels = np.arange(len(dimer))
+        self.labels = np.array(new_labels, dtype=np.int64)
+        self.bonds = np.array([Bond(dimer[i]) for i in range(len(dimer))], dtype=object)
+        self.rowrank = rowrank
+        return self
+
+    # ------------------------------------------------------------------ sectors ------
+    def GetTotalQnums(self, physical=False):
+        """UniTensor.py:2705-2873.  Returns (row-space Bond, col-space Bond) whose qnums are the fused
+        total charges, computed by the family-1 fusion kernel."""
+        if not self.is_symm:
+            raise TypeError("UniTensor.GetTotalQnums", "[ERROR] GetTotal Qnums from a non-symm tensor")
+        if physical:
+            sel_in = np.argwhere(self.braket == BondType[BD_KET]).flatten()
+            sel_out = np.argwhere(self.braket == BondType[BD_BRA]).flatten()
+            sg_in = np.ones(len(sel_in), dtype=np.int32)
+            sg_out = np.ones(len(sel_out), dtype=np.int32)
+        else:
+            sel_in = np.arange(self.rowrank)
+            sel_out = np.arange(self.rowrank, len(self.bonds))
+            sg_in = (self.braket[sel_in] * BondType[BD_KET]).astype(np.int32)
+            sg_out = (self.braket[sel_out] * BondType[BD_BRA]).astype(np.int32)
+        return (self._fused_bond(sel_in, sg_in, BD_KET), self._fused_bond(sel_out, sg_out, BD_BRA))
+
+    def _fused_bond(self, sel, signs, btype):
+        bonds = [self.bonds[i] for i in sel]
+        dims = _lib.i64([b.dim for b in bonds])
+        total = int(np.prod(dims, dtype=np.int64))
+        nsym = bonds[0].nsym
+        kinds, ns = _plan._sym_codes(bonds[0])
+        qoff = np.zeros(len(bonds), dtype=np.int64)
+        qoff[1:] = np.cumsum(dims[:-1])
+        dev = self._arena.device
+        with torch.cuda.device(dev):
+            d_q = torch.from_numpy(np.ascontiguousarray(np.concatenate([b.qnums for b in bonds], axis=0))).to(dev)
+            out = torch.empty((total, nsym), device=dev, dtype=torch.int64)
+            _lib.check(_lib.load().t10_fuse_qnums(len(bonds), nsym, _lib.np_ptr(dims), _lib.np_ptr(_lib.i32(signs)),
+                                                  _lib.np_ptr(kinds), _lib.np_ptr(ns), _lib.np_ptr(qoff), d_q.data_ptr(),
+                                                  out.data_ptr(), _lib.stream_ptr()))
+        bd = Bond.__new__(Bond)
+        bd.dim, bd.bondType, bd.nsym = total, btype, nsym
+        bd.sym_types = copy.copy(bonds[0].sym_types)
+        q = out.cpu().numpy()
+        q.setflags(write=False)
+        bd.qnums, bd._sig = q, None
+        return bd
+
+    def GetValidQnums(self, physical=False, return_shape=False):
+        """UniTensor.py:2875-2920"""
+        if physical:
+            b_in, b_out = self.GetTotalQnums(physical=True)
+            comm = _fx_GetCommRows(b_in.GetUniqueQnums(), b_out.GetUniqueQnums())
+            if return_shape:
+                shp = [np.array([b_in.GetDegeneracy(*q), b_out.GetDegeneracy(*q)]) for q in comm]
+                return comm, np.array(shp)
+            return comm
+        comm = copy.deepcopy(self._block_qnums)
+        if return_shape:
+            L = self._logical_layout()
+            return comm, np.stack([L.rows, L.cols], axis=1)
+        return comm
+
+    def _find_block(self, qnum, where):
+        if not self.is_symm:
+            raise TypeError(where, "[ERROR] Cannot get/put block on a non-symmetry tensor with qnums")
+        q = np.array(qnum).astype(np.int64)
+        if len(q) != self.bonds[0].nsym:
+            raise ValueError(where, "[ERROR] The qnumtum numbers not match the number of type.")
+        for s, row in enumerate(self._block_qnums):
+            if (row == q).all():
+                return s
+        raise TypeError(where, "[ERROR] No block has qnums:", qnum)
+
+    def PutBlock(self, block, *qnum):
+        """UniTensor.py:2922-3060.  Dense rank-2: Storage = block.Storage.  Symmetric: the sector with
+        these charges is overwritten (non-contiguous tensors scatter through the relayout kernel)."""
+        if not isinstance(block, self.__class__):
+            raise TypeError("UniTensor.PutBlock", "[ERROR] the block can only be an UniTensor")
+        if not self.is_symm:
+            if len(qnum):
+                raise TypeError("UniTensor.PutBlock", "[ERROR] Cannot put block with qnums on a non-symmetry tensor")
+            if self.is_diag != block.is_diag or tuple(self.shape) != tuple(block.shape):
+                raise Exception("UniTensor.PutBlock", "[ERROR] block shape / is_diag does not match the tensor")
+            self._dense = block._dense.clone()
+            return
+        if block.is_symm or block.is_diag or len(block.bonds) != 2:
+            raise TypeError("UniTensor.PutBlock", "[ERROR] the block must be a dense rank-2 UniTensor")
+        s = self._find_block(qnum, "UniTensor.PutBlock")
+        if self._contiguous:
+            dst = self._layout.views(self._arena_tensor())[s]
+            if tuple(dst.shape) != tuple(block._dense.shape):
+                raise TypeError("UniTensor.PutBlock", "[ERROR] the input block does not match the shape %s of the "
+                                                      "sector" % (tuple(dst.shape),))
+            dst.copy_(block._dense)
+            return
+        # logical view -> put -> scatter back into the memory layout (inverse relayout)
+        L = self._logical_layout()
+        logical = self.Contiguous()
+        dst = L.views(logical._arena)[s]
+        if tuple(dst.shape) != tuple(block._dense.shape):
+            raise TypeError("UniTensor.PutBlock", "[ERROR] the input block does not match the shape %s of the sector"
+                            % (tuple(dst.shape),))
+        dst.copy_(block._dense)
+        back = _plan.get_relayout(L, self._layout, self._inv_mapper, padded=False)
+        with torch.cuda.device(self._arena.device):
+            back.run(logical._arena, self._arena_tensor())
+
+    def GetBlock(self, *qnum):
+        """UniTensor.py:3062-3286: a COPY of the sector as an untagged rank-2 UniTensor."""
+        if not self.is_symm:
+            if len(qnum):
+                raise TypeError("UniTensor.GetBlock", "[ERROR] Cannot get block with qnums from a non-symmetry tensor")
+            if self.is_diag:
+                out = UniTensor(bonds=[Bond(self.bonds[0].dim), Bond(self.bonds[1].dim)], rowrank=1, check=False,
+                                is_diag=True)
+                out._mac(torch_tensor=self._dense.clone())
+                return out
+            x = self._contiguous_dense(self._dense)
+            x = x.clone() if x is self._dense else x
+            r = int(np.prod([b.dim for b in self.bonds[:self.rowrank]], dtype=np.int64))
+            out = UniTensor(bonds=[Bond(r), Bond(max(1, x.numel() // max(r, 1)))], rowrank=1, check=False)
+            out._mac(torch_tensor=x.reshape(r, -1))
+            return out
+        s = self._find_block(qnum, "UniTensor.GetBlock")
+        if self._contiguous:
+            blk = self._layout.views(self._arena_tensor())[s].clone()
+        else:
+            # gather only this sector through the relayout kernel (reference: per-element loop :3255-3273)
+            L = self._logical_layout()
+            plan = _plan.get_relayout(self._layout, L, self._mapper, padded=False, sectors=(s,))
+            src = self._arena_tensor()
+            with torch.cuda.device(src.device):
+                dst = L.new_arena(src.dtype, zero=False)
+                plan.run(src, dst)
+            blk = L.views(dst)[s].clone()
+        out = UniTensor(bonds=[Bond(blk.shape[0]), Bond(blk.shape[1])], rowrank=1, check=False)
+        out._mac(torch_tensor=blk)
+        return out
+
+    # ------------------------------------------------------------------ torch / autograd
+    def torch(self):
+        if self.is_symm:
+            raise Exception("[ERROR] cannot convert a symmetry tensor to torch.Tensor; use GetBlock")
+        return self._dense
+
+    def requires_grad(self, is_grad=None):
+        """The custom kernels are forward-only (no autograd graph through Contract)."""
+        st = self._arena if self.is_symm else self._dense
+        if is_grad is None:
+            return st.requires_grad
+        st.requires_grad_(bool(is_grad))
+        return self
+
+    def grad(self):
+        if self.is_symm:
+            raise Exception("[ERROR] grad of a symmetry tensor is not supported")
+        if self._dense.grad is None:
+            return None
+        return From_torch(self._dense.grad, rowrank=self.rowrank, labels=self.labels)
+
+    def backward(self):
+        if self.is_symm:
+            raise Exception("[ERROR] backward of a symmetry tensor is not supported")
+        self._dense.backward()
+
+    def detach(self):
+        if self.is_symm:
+            self._arena = self._arena_tensor().detach()
+            self._blocks = None
+        else:
+            self._dense = self._dense.detach()
+        return self
+
+    def __deepcopy__(self, memo):
+        t = UniTensor.__new__(UniTensor)
+        for k, v in self.__dict__.items():
+            if k == "_arena":
+                t._arena = None if v is None else self._arena_tensor().clone()
+            elif k == "_blocks":
+                t._blocks = None
+            elif k == "_layout":
+                t._layout = v
+            elif k == "_dense":
+                t._dense = None if v is None else v.clone()
+            elif k == "bonds":
+                t.bonds = np.array([copy.copy(b) for b in v], dtype=object)
+            else:
+                setattr(t, k, copy.deepcopy(v, memo))
+        return t
+
+
+# ======================================================================================
+def Save(a, filename):
+    if not isinstance(filename, str):
+        raise TypeError("Save", "[ERROR] Invalid filename.")
+    if not isinstance(a, UniTensor):
+        raise TypeError("Save", "[ERROR] input must be the UniTensor")
+    with open(filename + ".uniT", "wb") as f:
+        pickle.dump(a, f)
+
+
+def Load(filename):
+    if not isinstance(filename, str):
+        raise TypeError("UniTensor.Save", "[ERROR] Invalid filename.")
+    if not os.path.exists(filename):
+        raise Exception("UniTensor.Load", "[ERROR] file not exists")
+    with open(filename, "rb") as f:
+        tmp = pickle.load(f)
+    if not isinstance(tmp, UniTensor):
+        raise TypeError("Load", "[ERROR] loaded object is not the UniTensor")
+    return tmp
+
+
+def _dense_gemm(A2, B2):
+    """[M,K] x [K,N] on the family-3 kernel (single-problem group)."""
+    M, K = A2.shape
+    N = B2.shape[1]
+    _lib.require_cuda_tensor(A2, "contraction")
+    if B2.dtype != A2.dtype:
+        raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (A2.dtype, B2.dtype))
+    out = torch.empty((M, N), device=A2.device, dtype=A2.dtype)
+    if M * N == 0:
+        return out
+    if K == 0:
+        return out.zero_()
+    key = ("dense", M, N, K, A2.dtype, _plan._dev_index(A2.device))
+    grp = _plan._CONTRACTS.get(key)
+    if grp is None:
+        prob = np.zeros(1, dtype=_lib.GEMM_PROBLEM_DTYPE)
+        prob[0] = (0, 0, 0, M, N, K, K, N, N)
+        grp = _plan.GemmGroup(prob, A2.device, A2.dtype)
+        _plan._CONTRACTS[key] = grp
+    with torch.cuda.device(A2.device):
+        grp.run(A2, B2, out)
+    return out
+
+
+def _tensordot(ta, tb, a_ind, b_ind):
+    """torch.tensordot(ta, tb, dims=(a_ind, b_ind)) on the family-2 permute + family-3 GEMM kernels."""
+    a_free = [i for i in range(ta.dim()) if i not in set(a_ind)]
+    b_free = [i for i in range(tb.dim()) if i not in set(b_ind)]
+    A = UniTensor._contiguous_dense(ta.permute(a_free + list(a_ind)))
+    B = UniTensor._contiguous_dense(tb.permute(list(b_ind) + b_free))
+    K = 1
+    for i in a_ind:
+        K *= ta.shape[i]
+    M = A.numel() // max(K, 1) if K else int(np.prod([ta.shape[i] for i in a_free], dtype=np.int64))
+    N = B.numel() // max(K, 1) if K else int(np.prod([tb.shape[i] for i in b_free], dtype=np.int64))
+    out = _dense_gemm(A.reshape(M, K), B.reshape(K, N))
+    return out.reshape([ta.shape[i] for i in a_free] + [tb.shape[i] for i in b_free])
+
+
+def Contract(a, b):
+    """Contract two UniTensors over their common labels (UniTensor.py:3505-3880)."""
+    if not (isinstance(a, UniTensor) and isinstance(b, UniTensor)):
+        raise Exception("Contract(a,b)", "[ERROR] a and b both have to be UniTensor")
+    if (a.is_symm != b.is_symm) or ((a.braket is None) != (b.braket is None)):
+        raise TypeError("Contract(a,b)", "[ERROR] the tensors should be the same type to be contracted")
+
+    if a.is_symm:
+        return _plan.get_contract_plan(a, b).run(a, b)
+
+    same, a_ind, b_ind, a_free, b_free = _plan.label_match(a.labels, b.labels)
+    # diagonal operands are densified (UniTensor.py:3756-3765)
+    tmpa = torch.diag(a._dense) if a.is_diag else a._dense
+    tmpb = torch.diag(b._dense) if b.is_diag else b._dense
+    if len(same):
+        if a.braket is not None:
+            if False in np.unique((a.braket[a_ind] + b.braket[b_ind]) == 0):
+                raise Exception("Contract(a,b)", "[ERROR] bra-bond can only contract with ket-bond")
+        tmp = _tensordot(tmpa, tmpb, a_ind.tolist(), b_ind.tolist())
+        new_bonds = np.concatenate([copy.deepcopy(a.bonds[a_free]), copy.deepcopy(b.bonds[b_free])])
+        new_io = [(int(x) >= a.rowrank) for x in a_free] + [(int(x) >= b.rowrank) for x in b_free]
+        new_labels = np.concatenate([a.labels[a_free], b.labels[b_free]])
+        new_braket = None if a.braket is None else np.concatenate([a.braket[a_free], b.braket[b_free]])
+    else:
+        # outer product (UniTensor.py:3825-3880): rank-1 GEMM [M,1]x[1,N]
+        _lib.require_cuda_tensor(tmpa, "contraction")
+        A2 = UniTensor._contiguous_dense(tmpa).reshape(-1, 1)
+        B2 = UniTensor._contiguous_dense(tmpb).reshape(1, -1)
+        tmp = _dense_gemm(A2, B2).reshape(list(tmpa.shape) + list(tmpb.shape))
+        new_bonds = np.concatenate([copy.deepcopy(a.bonds), copy.deepcopy(b.bonds)])
+        new_io = [(x >= a.rowrank) for x in range(len(a.bonds))] + [(x >= b.rowrank) for x in range(len(b.bonds))]
+        new_labels = np.concatenate([a.labels, b.labels])
+        new_braket = None if a.braket is None else np.concatenate([a.braket, b.braket])
+    new_io = np.array(new_io, dtype=bool)
+    if len(new_labels):
+        # rows-first reorder, lazily (UniTensor.py:3773-3784).  np.argsort of booleans in the reference is
+        # stable for the ranks that occur; stated explicitly here.
+        mapper = np.argsort(new_io, kind="stable")
+        new_bonds = new_bonds[mapper]
+        new_labels = new_labels[mapper]
+        if new_braket is not None:
+            new_braket = new_braket[mapper]
+        tmp = tmp.permute(*[int(m) for m in mapper])
+    out = UniTensor(bonds=new_bonds, labels=new_labels, rowrank=int((~new_io).sum()), check=False)
+    out._mac(braket=new_braket, torch_tensor=tmp)
+    return out
+
+
+def _CombineBonds(a, idxs, new_label, permute_back):
+    """UniTensor.py:3967-4207, dense tensors.  (Symmetric CombineBonds is a 'next' row of SURVEY 8f.)"""
+    if not isinstance(a, UniTensor):
+        raise Exception("_CombineBonds(UniTensor,int_arr)", "[ERROR] )CombineBonds can only accept UniTensor")
+    if a.is_diag:
+        raise TypeError("_CombineBonds", "[ERROR] CombineBonds doesn't support diagonal matrix.")
+    if len(idxs) == 1:
+        return
+    if a.is_symm:
+        raise NotImplementedError("tor10_b200: CombineBonds on symmetric tensors is not built yet (SURVEY 8f-4)")
+    idx_no_combine = np.setdiff1d(np.arange(len(a.labels)), idxs)
+    old_shape = np.array(a.shape)
+    combined_dim = int(np.prod(old_shape[idxs]))
+    if new_label is not None:
+        newlbl = int(new_label)
+        if newlbl in a.labels[idx_no_combine] or newlbl in a.labels[idxs[1:]]:
+            raise Exception("_CombineBonds", "[ERROR], cannot set new_label to %d as there will be duplicate bond with "
+                                             "this label after combined" % newlbl)
+        a.labels[idxs[0]] = newlbl
+    new_bond = copy.copy(a.bonds[idxs[0]])
+    new_bond.combine(list(a.bonds[idxs[1:]]))
+    if a.braket is not None and not all(a.braket[i] == a.braket[idxs[0]] for i in idxs):
+        raise Exception("_CombineBonds", "[ERROR] cannot combine bonds with different bra/ket tags")
+    if permute_back:
+        # combined bond stays at the position of idxs[0]
+        pos = int(np.sum(idx_no_combine < idxs[0]))
+        order = list(idx_no_combine[:pos]) + list(idxs) + list(idx_no_combine[pos:])
+        x = UniTensor._contiguous_dense(a._dense.permute(*[int(i) for i in order]))
+        shp = list(old_shape[idx_no_combine[:pos]]) + [combined_dim] + list(old_shape[idx_no_combine[pos:]])
+        a._dense = x.reshape([int(s) for s in shp])
+        a.labels = np.concatenate([a.labels[idx_no_combine[:pos]], a.labels[idxs[:1]], a.labels[idx_no_combine[pos:]]])
+        a.bonds = np.array(list(a.bonds[idx_no_combine[:pos]]) + [new_bond] + list(a.bonds[idx_no_combine[pos:]]),
+                           dtype=object)
+        if a.braket is not None:
+            a.braket = np.concatenate([a.braket[idx_no_combine[:pos]], a.braket[idxs[:1]],
+                                       a.braket[idx_no_combine[pos:]]])
+        n_row_removed = int(np.sum(idxs[1:] < a.rowrank))
+        a.rowrank = a.rowrank - n_row_removed if idxs[0] < a.rowrank else a.rowrank - int(np.sum(idxs < a.rowrank))
+    else:
+        # combined bond goes first if idxs[0] is in row space, else last (UniTensor.py:4126-4180)
+        to_front = idxs[0] < a.rowrank
+        n_row = int(np.sum(idx_no_combine < a.rowrank))
+        if to_front:
+            order = list(idxs) + list(idx_no_combine)
+            shp = [combined_dim] + list(old_shape[idx_no_combine])
+            a.labels = np.concatenate([a.labels[idxs[:1]], a.labels[idx_no_combine]])
+            a.bonds = np.array([new_bond] + list(a.bonds[idx_no_combine]), dtype=object)
+            if a.braket is not None:
+                a.braket = np.concatenate([a.braket[idxs[:1]], a.braket[idx_no_combine]])
+            a.rowrank = n_row + 1
+        else:
+            order = list(idx_no_combine) + list(idxs)
+            shp = list(old_shape[idx_no_combine]) + [combined_dim]
+            a.labels = np.concatenate([a.labels[idx_no_combine], a.labels[idxs[:1]]])
+            a.bonds = np.array(list(a.bonds[idx_no_combine]) + [new_bond], dtype=object)
+            if a.braket is not None:
+                a.braket = np.concatenate([a.braket[idx_no_combine], a.braket[idxs[:1]]])
+            a.rowrank = n_row
+        x = UniTensor._contiguous_dense(a._dense.permute(*[int(i) for i in order]))
+        a._dense = x.reshape([int(s) for s in shp])
+    a._check_braket()
+
+
+def _Randomize(a):
+    """U[0,1) in every stored element (UniTensor.py:4210-4229)."""
+    if not isinstance(a, UniTensor):
+        raise Exception("_Randomize(UniTensor)", "[ERROR] _Randomize can only accept UniTensor")
+    if a.is_symm:
+        arena = a._arena_tensor()
+        arena.copy_(torch.rand(arena.shape, device=arena.device, dtype=arena.dtype))
+    else:
+        a._dense = torch.rand(a._dense.shape, dtype=a._dense.dtype, device=a._dense.device)
+
+
+def From_torch(torch_tensor, rowrank=None, labels=None, is_tag=False):
+    """UniTensor.py:4231-4322"""
+    if not isinstance(torch_tensor, torch.Tensor):
+        raise TypeError("From_torch", "[ERROR] can only accept torch.Tensor")
+    shape = torch_tensor.shape
+    if rowrank is not None:
+        if rowrank > len(shape) or rowrank < 0:
+            raise ValueError("From_torch", "[ERROR] rowrank exceed the rank of input torch.Tensor.")
+    else:
+        if len(shape) != 0:
+            raise ValueError("From_torch", "[ERROR] rowrank must be set for a non rank-0 tensor")
+        rowrank = 0
+    if labels is not None and len(labels) != len(shape):
+        raise TypeError("From_torch", "[ERROR] # of labels should match the rank of torch.Tensor")
+    if is_tag:
+        new_bonds = [Bond(shape[i], BD_KET) for i in range(rowrank)] + \
+                    [Bond(shape[i + rowrank], BD_BRA) for i in range(len(shape) - rowrank)]
+    else:
+        new_bonds = [Bond(shape[i]) for i in range(len(shape))]
+    if len(new_bonds) == 0:
+        tmp = UniTensor(bonds=[], labels=[], rowrank=0, check=False)
+        tmp._mac(torch_tensor=torch_tensor)
+        return tmp
+    out = UniTensor(bonds=new_bonds, labels=labels, rowrank=int(rowrank), check=False)
+    braket = np.array([BondType[b.bondType] for b in new_bonds], dtype=np.int64) if is_tag else None
+    out._mac(torch_tensor=torch_tensor, braket=braket)
+    return out

@@ -1,0 +1,436 @@
+"""Plans: everything about a symmetric tensor layout / a relayout / a contraction that depends only
+on bond signatures, labels and row ranks -- computed once (device kernels of family 1), cached,
+and then replayed with zero host bookkeeping per call.
+
+  BlockLayout    block map of (bonds, braket, rowrank)         <- UniTensor.__init__ :393-441
+  RelayoutPlan   address tables + tile list M -> L              <- UniTensor.Contiguous :2097-2129
+  ContractPlan   relayouts + sector matching + GEMM tile table  <- Contract :3686-3743
+
+The reference recomputes all of this with numpy on every call (3 block-map builds, 2 deepcopies and
+an O(nsec^2) sector search per Contract).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ARENA_ALIGN, RELAYOUT_TC, RELAYOUT_TR, check, i32, i64, np_ptr
+
+_LAYOUTS = {}
+_RELAYOUTS = {}
+_CONTRACTS = {}
+STATS = {"layout_build": 0, "relayout_build": 0, "contract_build": 0}
+
+
+def clear_caches():
+    _LAYOUTS.clear()
+    _RELAYOUTS.clear()
+    _CONTRACTS.clear()
+
+
+def _dev_index(device):
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+def _sym_codes(bond):
+    kinds = i32([s._code()[0] for s in bond.sym_types])
+    ns = i64([s._code()[1] for s in bond.sym_types])
+    return kinds, ns
+
+
+def accu_offsets(dims, rowrank):
+    """UniTensor.py:396-403"""
+    accu = np.ones(len(dims), dtype=np.int64)
+    for i in range(len(dims) - 2, -1, -1):
+        accu[i] = accu[i + 1] * int(dims[i + 1])
+    accu_in = (accu[:rowrank] // accu[rowrank - 1]).astype(np.int64)
+    accu_out = accu[rowrank:].astype(np.int64)
+    return accu_in, accu_out
+
+
+class BlockLayout:
+    """Device-resident block map of one (bonds, braket, rowrank) signature."""
+
+    def __init__(self, bonds, braket, rowrank, device):
+        lib = _lib.load()
+        device = _lib.require_cuda(device)
+        STATS["layout_build"] += 1
+        self.device = device
+        self.rank = len(bonds)
+        self.rowrank = int(rowrank)
+        self.nsym = int(bonds[0].nsym)
+        self.dims = i64([b.dim for b in bonds])
+        self.braket = i32(braket)
+        self.accu_in, self.accu_out = accu_offsets(self.dims, self.rowrank)
+        self.R = int(np.prod(self.dims[:rowrank], dtype=np.int64))
+        self.C = int(np.prod(self.dims[rowrank:], dtype=np.int64))
+        kinds, ns = _sym_codes(bonds[0])
+        self.all_u1 = bool((kinds == 0).all())
+        qoff = np.zeros(self.rank, dtype=np.int64)
+        qoff[1:] = np.cumsum(self.dims[:-1])
+        qcat = np.concatenate([b.qnums for b in bonds], axis=0)
+        with torch.cuda.device(device):
+            d_q = torch.from_numpy(np.ascontiguousarray(qcat)).to(device)
+            cap = min(self.R, self.C)
+            opt = dict(device=device, dtype=torch.int64)
+            self.d_block_qnums = torch.empty((cap, self.nsym), **opt)
+            self.d_ket_map = torch.empty((self.R, 2), **opt)
+            self.d_bra_map = torch.empty((self.C, 2), **opt)
+            self.d_ket_idx = torch.empty((self.R,), **opt)
+            self.d_bra_idx = torch.empty((self.C,), **opt)
+            self.d_sec_info = torch.empty((cap, 8), **opt)
+            self.d_rowbase = torch.empty((self.R,), **opt)
+            self.d_coloff = torch.empty((self.C,), device=device, dtype=torch.int32)
+            counts = np.zeros(4, dtype=np.int64)
+            check(lib.t10_blockmap_build(
+                self.rank, self.rowrank, self.nsym, np_ptr(self.dims), np_ptr(self.braket), np_ptr(kinds),
+                np_ptr(ns), np_ptr(qoff), d_q.data_ptr(), cap, self.d_block_qnums.data_ptr(),
+                self.d_ket_map.data_ptr(), self.d_bra_map.data_ptr(), self.d_ket_idx.data_ptr(),
+                self.d_bra_idx.data_ptr(), self.d_sec_info.data_ptr(), self.d_rowbase.data_ptr(),
+                self.d_coloff.data_ptr(), np_ptr(counts), _lib.stream_ptr()))
+        self.nsec = int(counts[0])
+        self.arena_elems = int(counts[1])
+        self.n_ket = int(counts[2])
+        self.n_bra = int(counts[3])
+        self.d_block_qnums = self.d_block_qnums[:self.nsec]
+        self.d_sec_info = self.d_sec_info[:self.nsec]
+        self.d_ket_idx = self.d_ket_idx[:self.n_ket]
+        self.d_bra_idx = self.d_bra_idx[:self.n_bra]
+        self.block_qnums = self.d_block_qnums.cpu().numpy()            # [nsec, nsym] ascending lex
+        info = self.d_sec_info.cpu().numpy()
+        self.rows = info[:, 0].copy()
+        self.cols = info[:, 1].copy()
+        self.ket_start = info[:, 2].copy()
+        self.bra_start = info[:, 3].copy()
+        self.arena_off = info[:, 4].copy()
+        self.nnz = int((self.rows * self.cols).sum())
+        self._qindex = {tuple(q): i for i, q in enumerate(self.block_qnums.tolist())}
+        self._host = {}
+
+    # ---- host mirrors in the reference's attribute format (lazy) -------------------
+    def host(self, name):
+        if name not in self._host:
+            if name == "ket_map":
+                v = self.d_ket_map.cpu().numpy()
+            elif name == "bra_map":
+                v = self.d_bra_map.cpu().numpy()
+            elif name in ("ket_inv", "bra_inv"):
+                idx = self.d_ket_idx if name == "ket_inv" else self.d_bra_idx
+                strides = self.accu_in if name == "ket_inv" else self.accu_out
+                start = self.ket_start if name == "ket_inv" else self.bra_start
+                cnt = self.rows if name == "ket_inv" else self.cols
+                out = torch.empty((idx.numel(), len(strides)), device=self.device, dtype=torch.int64)
+                with torch.cuda.device(self.device):
+                    check(_lib.load().t10_unravel(idx.numel(), len(strides), np_ptr(i64(strides)), idx.data_ptr(),
+                                                  out.data_ptr(), _lib.stream_ptr()))
+                h = out.cpu().numpy()
+                v = [h[int(start[b]):int(start[b] + cnt[b])] for b in range(self.nsec)]
+            else:
+                raise KeyError(name)
+            self._host[name] = v
+        return self._host[name]
+
+    def sector_of(self, qnum):
+        return self._qindex.get(tuple(int(x) for x in qnum))
+
+    def new_arena(self, dtype, zero=True):
+        n = self.arena_elems + ARENA_ALIGN
+        return (torch.zeros if zero else torch.empty)(n, device=self.device, dtype=dtype)
+
+    def views(self, arena):
+        return [arena[int(o):int(o + r * c)].view(int(r), int(c))
+                for o, r, c in zip(self.arena_off, self.rows, self.cols)]
+
+
+def layout_signature(bonds, braket, rowrank):
+    return (tuple(b.signature()[0:1] + b.signature()[2:] for b in bonds), tuple(int(x) for x in braket), int(rowrank))
+
+
+def get_layout(bonds, braket, rowrank, device):
+    key = (layout_signature(bonds, braket, rowrank), _dev_index(device))
+    lay = _LAYOUTS.get(key)
+    if lay is None:
+        lay = BlockLayout(bonds, braket, rowrank, device)
+        lay.key = key
+        _LAYOUTS[key] = lay
+    return lay
+
+
+# ------------------------------------------------------------------------------------
+class PackedLayout:
+    """Where a relayout writes: sector offsets / leading dimensions of the destination buffer.
+    `native(L)` is the tensor's own arena; `padded(L)` is the GEMM-operand scratch with even
+    leading dimensions (16-byte rows for the cp.async loader)."""
+
+    def __init__(self, off, ld, size):
+        self.off, self.ld, self.size = i64(off), i64(ld), int(size)
+
+    @staticmethod
+    def native(L):
+        return PackedLayout(L.arena_off, L.cols, L.arena_elems + ARENA_ALIGN)
+
+    @staticmethod
+    def padded(L):
+        ld = (L.cols + 1) // 2 * 2
+        sz = (L.rows * ld + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+        off = np.zeros(L.nsec, dtype=np.int64)
+        off[1:] = np.cumsum(sz)[:-1]
+        return PackedLayout(off, ld, int(sz.sum()) + ARENA_ALIGN)
+
+
+class RelayoutPlan:
+    """src layout M --(mapper)--> dst layout L, optionally restricted to some dst sectors."""
+
+    def __init__(self, M, L, mapper, packed, sectors=None):
+        lib = _lib.load()
+        STATS["relayout_build"] += 1
+        self.M, self.L, self.packed = M, L, packed
+        self.check = not M.all_u1      # U1 charges are conserved exactly; Zn layouts can lose sectors (Q3)
+        dev = L.device
+        mapper = [int(x) for x in mapper]
+        rank = L.rank
+        # logical position p sits at memory position mapper[p]; its digit moves the source flat row
+        # (if that memory position is in M's row space) or the source flat column.
+        srow = np.zeros(rank, dtype=np.int64)
+        scol = np.zeros(rank, dtype=np.int64)
+        for p in range(rank):
+            mp = mapper[p]
+            if mp < M.rowrank:
+                srow[p] = M.accu_in[mp]
+            else:
+                scol[p] = M.accu_out[mp - M.rowrank]
+        rr = L.rowrank
+        o32 = dict(device=dev, dtype=torch.int32)
+        self.RR = torch.empty(L.n_ket, **o32)
+        self.RC = torch.empty(L.n_ket, **o32)
+        self.CR = torch.empty(L.n_bra, **o32)
+        self.CC = torch.empty(L.n_bra, **o32)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr()
+            check(lib.t10_relayout_tables(L.n_ket, rr, np_ptr(i64(L.dims[:rr])), np_ptr(i64(srow[:rr])),
+                                          np_ptr(i64(scol[:rr])), L.d_ket_idx.data_ptr(), self.RR.data_ptr(),
+                                          self.RC.data_ptr(), st))
+            check(lib.t10_relayout_tables(L.n_bra, rank - rr, np_ptr(i64(L.dims[rr:])), np_ptr(i64(srow[rr:])),
+                                          np_ptr(i64(scol[rr:])), L.d_bra_idx.data_ptr(), self.CR.data_ptr(),
+                                          self.CC.data_ptr(), st))
+        sec = np.zeros((L.nsec, 8), dtype=np.int64)
+        sec[:, 0], sec[:, 1], sec[:, 2], sec[:, 3] = L.rows, L.cols, L.ket_start, L.bra_start
+        sec[:, 4], sec[:, 5] = packed.off, packed.ld
+        self.d_sec = torch.from_numpy(sec).to(dev)
+        tiles = []
+        for s in (range(L.nsec) if sectors is None else sectors):
+            r, c = int(L.rows[s]), int(L.cols[s])
+            nr, nc = -(-r // RELAYOUT_TR), -(-c // RELAYOUT_TC)
+            if nr * nc == 0:
+                continue
+            t = np.zeros((nr, nc, 4), dtype=np.int32)
+            t[:, :, 0] = s
+            t[:, :, 1] = (np.arange(nr, dtype=np.int32) * RELAYOUT_TR)[:, None]
+            t[:, :, 2] = (np.arange(nc, dtype=np.int32) * RELAYOUT_TC)[None, :]
+            tiles.append(t.reshape(-1, 4))
+        tiles = np.concatenate(tiles) if tiles else np.zeros((0, 4), dtype=np.int32)
+        self.ntiles = len(tiles)
+        self.d_tiles = torch.from_numpy(tiles).to(dev)
+        self.moved_elems = int(sum(int(L.rows[s]) * int(L.cols[s])
+                                   for s in (range(L.nsec) if sectors is None else sectors)))
+
+    def run(self, src_arena, dst):
+        """dst must hold packed.size elements; padding/unmatched space is left untouched."""
+        check(_lib.load().t10_relayout_blocks(
+            _lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(), self.ntiles,
+            self.d_tiles.data_ptr(), self.d_sec.data_ptr(), self.RR.data_ptr(), self.RC.data_ptr(),
+            self.CR.data_ptr(), self.CC.data_ptr(), self.M.d_rowbase.data_ptr(), self.M.d_coloff.data_ptr(),
+            self.M.d_ket_map.data_ptr() if self.check else None, self.M.d_bra_map.data_ptr() if self.check else None,
+            _lib.stream_ptr()))
+        return dst
+
+
+def get_relayout(M, L, mapper, padded=False, sectors=None):
+    key = (M.key, L.key, tuple(int(x) for x in mapper), bool(padded), None if sectors is None else tuple(sectors))
+    pl = _RELAYOUTS.get(key)
+    if pl is None:
+        packed = PackedLayout.padded(L) if padded else PackedLayout.native(L)
+        pl = RelayoutPlan(M, L, mapper, packed, sectors)
+        _RELAYOUTS[key] = pl
+    return pl
+
+
+# ------------------------------------------------------------------------------------
+def label_match(la, lb):
+    """np.intersect1d(..., return_indices=True) + setdiff1d (UniTensor.py:3686-3689): common labels
+    in ASCENDING label order (quirk Q5), their positions, and the free positions ascending."""
+    same, a_ind, b_ind = np.intersect1d(la, lb, return_indices=True)
+    a_free = np.setdiff1d(np.arange(len(la)), a_ind)
+    b_free = np.setdiff1d(np.arange(len(lb)), b_ind)
+    return same, a_ind.astype(np.int64), b_ind.astype(np.int64), a_free.astype(np.int64), b_free.astype(np.int64)
+
+
+def pick_tile_cfg(problems):
+    """64x64 tiles unless the group is dominated by large GEMMs that fill >= 2 waves of 128x128."""
+    import os
+    forced = os.environ.get("TOR10_GGEMM_CFG")
+    if forced is not None:
+        return int(forced)
+    n128 = sum((-(-int(p["m"]) // 128)) * (-(-int(p["n"]) // 128)) for p in problems
+               if p["m"] >= 96 and p["n"] >= 96)
+    big = sum(int(p["m"]) * int(p["n"]) * int(p["k"]) for p in problems if p["m"] >= 96 and p["n"] >= 96)
+    tot = sum(int(p["m"]) * int(p["n"]) * int(p["k"]) for p in problems) or 1
+    if n128 >= 2 * 148 and big > 0.9 * tot:
+        return 1
+    return 0
+
+
+class GemmGroup:
+    """Problem table + tile table on the device."""
+
+    def __init__(self, problems, device, dtype, tile_cfg=None):
+        lib = _lib.load()
+        self.problems = np.ascontiguousarray(problems, dtype=_lib.GEMM_PROBLEM_DTYPE)
+        self.nprob = len(self.problems)
+        self.dtype_code = _lib.dtype_code(dtype)
+        if tile_cfg is None:
+            tile_cfg = pick_tile_cfg(self.problems) if dtype == torch.float64 else 0
+        self.tile_cfg = int(tile_cfg)
+        plan_cfg = 0 if self.tile_cfg == 100 else self.tile_cfg
+        nt = C.c_int64(0)
+        check(lib.t10_ggemm_plan_tiles(plan_cfg, self.nprob, np_ptr(self.problems), 0, None, C.byref(nt)))
+        tiles = np.zeros((max(nt.value, 1), 4), dtype=np.int32)
+        check(lib.t10_ggemm_plan_tiles(plan_cfg, self.nprob, np_ptr(self.problems), nt.value, np_ptr(tiles),
+                                       C.byref(nt)))
+        self.ntiles = int(nt.value)
+        self.d_tiles = torch.from_numpy(tiles).to(device)
+        self.d_prob = torch.from_numpy(self.problems.view(np.uint8).reshape(-1)).to(device) if self.nprob else \
+            torch.zeros(48, dtype=torch.uint8, device=device)
+        self.flops = float(sum(2.0 * int(p["m"]) * int(p["n"]) * int(p["k"]) for p in self.problems))
+        self.bytes = float(sum(int(p["m"]) * int(p["k"]) + int(p["k"]) * int(p["n"]) + int(p["m"]) * int(p["n"])
+                               for p in self.problems))
+
+    def run(self, A, B, Cc):
+        check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
+                                    self.nprob, self.d_prob.data_ptr(), self.ntiles, self.d_tiles.data_ptr(),
+                                    _lib.stream_ptr()))
+
+
+class ContractPlan:
+    """Symmetric Contract(a, b): UniTensor.py:3692-3743."""
+
+    def __init__(self, a, b, shard=None):
+        from .Bond import BondType, BD_KET
+        STATS["contract_build"] += 1
+        self.shard = shard
+        same, a_ind, b_ind, a_free, b_free = label_match(a.labels, b.labels)
+        if len(same) == 0:
+            raise Exception("Developing")                                          # :3745-3747 (Q6)
+        if ((a.braket[a_ind] + b.braket[b_ind]) != 0).any():                        # :3700-3701
+            raise Exception("Contract(a,b)", "[ERROR] bra-bond can only contract with ket-bond")
+        dev = a.device
+        perm_a = np.append(a_free, a_ind)
+        perm_b = np.append(b_ind, b_free)
+        rr_a, rr_b = len(a_free), len(b_ind)
+        if rr_a < 1 or len(b_free) < 1:
+            # the reference builds `out` from zero row (col) bonds and fails in UniTensor.__init__
+            raise TypeError("UniTensor.__init__", "[ERROR] tensor with symmetry must have at least one rank for "
+                                                  "row space and one rank for column space")
+        bonds_a = [a.bonds[i] for i in perm_a]
+        bonds_b = [b.bonds[i] for i in perm_b]
+        bk_a, bk_b = a.braket[perm_a], b.braket[perm_b]
+        map_a, map_b = a._mapper[perm_a], b._mapper[perm_b]
+        Ma, Mb = a._layout, b._layout
+        La = get_layout(bonds_a, bk_a, rr_a, dev)
+        Lb = get_layout(bonds_b, bk_b, rr_b, dev)
+        # output: a's free bonds then b's free bonds; rowrank INFERRED as #KET (quirk Q2, :3720-3723)
+        self.out_bonds = bonds_a[:rr_a] + bonds_b[rr_b:]
+        self.out_labels = np.append(a.labels[perm_a][:rr_a], b.labels[perm_b][rr_b:])
+        self.out_braket = np.append(bk_a[:rr_a], bk_b[rr_b:])
+        self.out_rowrank = int((self.out_braket == BondType[BD_KET]).sum())
+        if self.out_rowrank < 1 or self.out_rowrank >= len(self.out_bonds):
+            raise TypeError("UniTensor.__init__", "[ERROR] tensor with symmetry must have at least one rank for "
+                                                  "row space and one rank for column space")
+        Lo = get_layout(self.out_bonds, self.out_braket, self.out_rowrank, dev)
+        self.La, self.Lb, self.Lo = La, Lb, Lo
+        # the reference tests only `_mapper == identity` (quirk Q1); a changed rowrank with identity
+        # mapper leaves its Storage stale.  Here the relayout runs whenever the memory layout differs.
+        ident_a = (map_a == np.arange(len(map_a))).all() and rr_a == Ma.rowrank
+        ident_b = (map_b == np.arange(len(map_b))).all() and rr_b == Mb.rowrank
+        # sector matching (UniTensor.py:3727-3738)
+        matched = []
+        for ob in range(Lo.nsec):
+            ab = La.sector_of(Lo.block_qnums[ob])
+            bb = Lb.sector_of(Lo.block_qnums[ob])
+            if ab is not None and bb is not None:
+                ma, ka, kb, nb = int(La.rows[ab]), int(La.cols[ab]), int(Lb.rows[bb]), int(Lb.cols[bb])
+                if ka != kb or ma != int(Lo.rows[ob]) or nb != int(Lo.cols[ob]):
+                    # outside the well-defined domain (quirk Q2): the reference raises inside torch.matmul
+                    # or silently stores a block of the wrong shape
+                    raise RuntimeError("Contract(a,b): sector %s has mismatched block shapes A[%d,%d] B[%d,%d] "
+                                       "out[%d,%d] (row/col split of the result differs from the operands')"
+                                       % (Lo.block_qnums[ob].tolist(), ma, ka, kb, nb, Lo.rows[ob], Lo.cols[ob]))
+                matched.append((ob, ab, bb))
+        self.all_matched = len(matched) == Lo.nsec
+        self.flops_total = float(sum(2.0 * int(La.rows[ab]) * int(La.cols[ab]) * int(Lb.cols[bb])
+                                     for _, ab, bb in matched))
+        self.ranges = None
+        if shard is not None:
+            # independent sectors are partitioned over the ranks: contiguous runs of output
+            # sectors with balanced flops, so that every rank's result is ONE slice of the arena
+            from .parallel import partition_contiguous, arena_ranges
+            rank, world = shard
+            cost = np.zeros(Lo.nsec)
+            for ob, ab, bb in matched:
+                cost[ob] = 2.0 * int(La.rows[ab]) * int(La.cols[ab]) * int(Lb.cols[bb])
+            bounds = partition_contiguous(cost, world)
+            self.sector_bounds = bounds
+            self.ranges = arena_ranges(Lo, bounds)
+            matched = [m for m in matched if bounds[rank] <= m[0] < bounds[rank + 1]]
+        self.matched = matched
+        sec_a = sorted(set(m[1] for m in matched))
+        sec_b = sorted(set(m[2] for m in matched))
+        self.rel_a = None if ident_a else get_relayout(Ma, La, map_a, padded=True, sectors=sec_a)
+        self.rel_b = None if ident_b else get_relayout(Mb, Lb, map_b, padded=True, sectors=sec_b)
+        pa = self.rel_a.packed if self.rel_a else PackedLayout.native(La)
+        pb = self.rel_b.packed if self.rel_b else PackedLayout.native(Lb)
+        prob = np.zeros(len(matched), dtype=_lib.GEMM_PROBLEM_DTYPE)
+        for i, (ob, ab, bb) in enumerate(matched):
+            prob[i] = (pa.off[ab], pb.off[bb], Lo.arena_off[ob], La.rows[ab], Lb.cols[bb], La.cols[ab],
+                       pa.ld[ab], pb.ld[bb], Lo.cols[ob])
+        self.gemm = GemmGroup(prob, dev, a.dtype)
+        self.flops = self.gemm.flops
+        self.gemm_bytes = self.gemm.bytes
+
+    def run(self, a, b):
+        from .UniTensor import UniTensor
+        dt = a.dtype
+        if b.dtype != dt:
+            raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (dt, b.dtype))
+        with torch.cuda.device(a.device):
+            A = a._arena_tensor()
+            B = b._arena_tensor()
+            if self.rel_a is not None:
+                A = self.rel_a.run(A, torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt))
+            if self.rel_b is not None:
+                B = self.rel_b.run(B, torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt))
+            Cc = self.Lo.new_arena(dt, zero=not self.all_matched)
+            self.gemm.run(A, B, Cc)
+            if self.shard is not None and self.shard[1] > 1:
+                from .parallel import gather_ranges
+                gather_ranges(Cc, self.ranges, self.shard[0])
+        return UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.out_rowrank, self.Lo, Cc)
+
+
+def contract_key(a, b):
+    return (a._layout.key, tuple(a._mapper.tolist()), tuple(a.labels.tolist()), a.rowrank,
+            b._layout.key, tuple(b._mapper.tolist()), tuple(b.labels.tolist()), b.rowrank,
+            a.dtype, tuple(a.braket.tolist()), tuple(b.braket.tolist()))
+
+
+def get_contract_plan(a, b):
+    from . import parallel
+    shard = parallel.current_shard()
+    key = (contract_key(a, b), shard)
+    pl = _CONTRACTS.get(key)
+    if pl is None:
+        pl = ContractPlan(a, b, shard)
+        _CONTRACTS[key] = pl
+    return pl

@@ -1,0 +1,315 @@
+// Family 2: HBM-bound data movement.
+//
+//   t10_relayout_blocks  block-sparse strided permute between two sector layouts of the
+//                        same symmetric tensor (reference: the interpreted element loop of
+//                        UniTensor.Contiguous, UniTensor.py:2108-2129, ~4e4 elements/s).
+//   t10_permute_dense    dense N-d strided permute into a contiguous tensor
+//                        (reference: Tensor.contiguous(), UniTensor.py:2057/:2144, and the
+//                        implicit copy inside torch.tensordot, :3769).
+//   t10_diag_scale       row/column scaling by a diagonal operand (replaces torch.diag +
+//                        dense GEMM, UniTensor.py:3756-3765).
+//
+// Relayout formulation (gather form): the source address of destination
+// element (sector s, row r, col c) is additively separable into a row part and a column
+// part BEFORE the block-map lookup:
+//     src_row = RR[r] + CR[c]     src_col = RC[r] + CC[c]
+//     addr    = rowbase[src_row] + coloff[src_col]
+// RR/RC (per destination row) and CR/CC (per destination column) are small int32 tables
+// built once per plan (t10_relayout_tables); rowbase/coloff belong to the source layout
+// (t10_blockmap_build).  Every thread owns one destination column (coalesced stores, CR/CC
+// in registers) and walks the rows of its tile with the loads of several rows in flight.
+// Source sectors (32 B) touched by neighbouring rows of a tile are served from L1.
+#include <algorithm>
+
+#include "t10_common.cuh"
+
+namespace t10 {
+
+constexpr int RL_THREADS = 256;                 // 8 warps: 4 column groups x 2 row halves
+constexpr int RL_TR = T10_RELAYOUT_TR;          // 32 rows per tile
+constexpr int RL_TC = T10_RELAYOUT_TC;          // 128 columns per tile
+constexpr int RL_UNROLL = 8;
+
+template <typename T, bool CHECK>
+__global__ void __launch_bounds__(RL_THREADS)
+k_relayout_blocks(const T* __restrict__ src, T* __restrict__ dst, int64_t ntiles,
+                  const int4* __restrict__ tiles, const int64_t* __restrict__ dst_sec,
+                  const int32_t* __restrict__ RR, const int32_t* __restrict__ RC,
+                  const int32_t* __restrict__ CR, const int32_t* __restrict__ CC,
+                  const int64_t* __restrict__ rowbase, const int32_t* __restrict__ coloff,
+                  const int64_t* __restrict__ ket_map, const int64_t* __restrict__ bra_map) {
+  __shared__ int32_t s_rr[RL_TR], s_rc[RL_TR];
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int4 tile = tiles[t];
+    const int64_t* si = dst_sec + (int64_t)tile.x * 8;
+    const int rows = (int)si[0], cols = (int)si[1];
+    const int64_t ks = si[2], bs = si[3], doff = si[4], dld = si[5];
+    const int r0 = tile.y, c0 = tile.z;
+    const int nr = min(RL_TR, rows - r0);
+    __syncthreads();  // previous tile done with s_rr/s_rc
+    if (threadIdx.x < RL_TR) {
+      int r = threadIdx.x;
+      s_rr[r] = r < nr ? RR[ks + r0 + r] : 0;
+      s_rc[r] = r < nr ? RC[ks + r0 + r] : 0;
+    }
+    __syncthreads();
+    const int c = c0 + (threadIdx.x & (RL_TC - 1));
+    const int rbeg = (threadIdx.x / RL_TC) * (RL_TR / (RL_THREADS / RL_TC));
+    const int rend = min(nr, rbeg + RL_TR / (RL_THREADS / RL_TC));
+    if (c < cols) {
+      const int cr = CR[bs + c], cc = CC[bs + c];
+      T* out = dst + doff + (int64_t)r0 * dld + c;
+      for (int rb = rbeg; rb < rend; rb += RL_UNROLL) {
+        T v[RL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < RL_UNROLL; ++u) {
+          const int r = rb + u;
+          v[u] = T(0);
+          if (r < rend) {
+            const int64_t base = rowbase[s_rr[r] + cr];
+            const int32_t co = coloff[s_rc[r] + cc];
+            bool ok = base >= 0 && co >= 0;
+            if (CHECK && ok)  // Zn layouts (quirk Q3): row and column may sit in different sectors
+              ok = ket_map[2 * (int64_t)(s_rr[r] + cr)] == bra_map[2 * (int64_t)(s_rc[r] + cc)];
+            if (ok) v[u] = src[base + co];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RL_UNROLL; ++u) {
+          const int r = rb + u;
+          if (r < rend) out[(int64_t)r * dld] = v[u];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- dense permute ----
+struct PermDesc {
+  int rank;                       // collapsed rank, dst order (last = dst innermost)
+  int64_t shape[T10_MAX_RANK];
+  int64_t sstride[T10_MAX_RANK];  // source stride of each dst dim (elements)
+  int64_t total;
+};
+
+// dst innermost dim is also source-contiguous: vectorised row copy
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+k_permute_rows(const T* __restrict__ src, T* __restrict__ dst, const __grid_constant__ PermDesc pd) {
+  const int64_t inner = pd.shape[pd.rank - 1] / VEC;  // vectors per row
+  const int64_t nvec = pd.total / VEC;
+  struct alignas(sizeof(T) * VEC) Vec { T v[VEC]; };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / inner, iv = i - row * inner;
+    int64_t soff = 0;
+#pragma unroll 1
+    for (int d = pd.rank - 2; d >= 0; --d) {
+      int64_t q = row / pd.shape[d];
+      soff += (row - q * pd.shape[d]) * pd.sstride[d];
+      row = q;
+    }
+    *reinterpret_cast<Vec*>(dst + i * VEC) = *reinterpret_cast<const Vec*>(src + soff + iv * VEC);
+  }
+}
+
+// general case: 32x32 tile transposed through shared memory.  Tile axes: X = dst innermost
+// dim (coalesced stores), Y = the dst dim whose source stride is 1 (coalesced loads).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_permute_tiled(const T* __restrict__ src, T* __restrict__ dst, const __grid_constant__ PermDesc pd,
+                int ydim, int64_t tiles_x, int64_t tiles_y, int64_t ntiles) {
+  __shared__ T tile[32][33];
+  const int X = pd.rank - 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int64_t rem = t;
+    const int64_t bx = rem % tiles_x;
+    rem /= tiles_x;
+    const int64_t by = rem % tiles_y;
+    rem /= tiles_y;
+    // remaining dims (all but X and ydim), row-major over dst order
+    int64_t soff = 0, doff = 0, dstride = pd.shape[X];
+#pragma unroll 1
+    for (int d = pd.rank - 2; d >= 0; --d) {
+      if (d != ydim) {
+        int64_t q = rem / pd.shape[d];
+        int64_t i = rem - q * pd.shape[d];
+        soff += i * pd.sstride[d];
+        doff += i * dstride;
+        rem = q;
+      }
+      dstride *= pd.shape[d];
+    }
+    // dst stride of ydim
+    int64_t ystride_d = pd.shape[X];
+    for (int d = pd.rank - 2; d > ydim; --d) ystride_d *= pd.shape[d];
+    const int64_t x0 = bx * 32, y0 = by * 32;
+    __syncthreads();
+    // load: threads fastest along Y (source contiguous)
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      int64_t x = x0 + ty + j, y = y0 + tx;
+      if (x < pd.shape[X] && y < pd.shape[ydim])
+        tile[ty + j][tx] = src[soff + x * pd.sstride[X] + y * pd.sstride[ydim]];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      int64_t y = y0 + ty + j, x = x0 + tx;
+      if (x < pd.shape[X] && y < pd.shape[ydim]) dst[doff + y * ystride_d + x] = tile[tx][ty + j];
+    }
+  }
+}
+
+// fallback for shapes without a unit-stride source dim: plain gather, coalesced stores
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_permute_gather(const T* __restrict__ src, T* __restrict__ dst, const __grid_constant__ PermDesc pd) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pd.total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, soff = 0;
+#pragma unroll 1
+    for (int d = pd.rank - 1; d >= 0; --d) {
+      int64_t q = rem / pd.shape[d];
+      soff += (rem - q * pd.shape[d]) * pd.sstride[d];
+      rem = q;
+    }
+    dst[i] = src[soff];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_diag_scale(const T* __restrict__ a, const T* __restrict__ diag, T* __restrict__ out,
+             int64_t rows, int64_t cols, int side) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols;
+    out[i] = a[i] * (side ? diag[i - r * cols] : diag[r]);
+  }
+}
+
+template <typename T>
+static int launch_permute(const T* src, T* dst, const PermDesc& pd, cudaStream_t st) {
+  const int last = pd.rank - 1;
+  const int grid_cap = sm_count() * 8;
+  if (pd.sstride[last] == 1) {
+    // row copy; widest vector that divides the row, all source strides and both pointers
+    int vec = (int)(16 / sizeof(T));
+    auto ok = [&](int v) {
+      if (pd.shape[last] % v) return false;
+      for (int d = 0; d < last; ++d)
+        if (pd.sstride[d] % v) return false;
+      return ((uintptr_t)src % (v * sizeof(T)) == 0) && ((uintptr_t)dst % (v * sizeof(T)) == 0);
+    };
+    while (vec > 1 && !ok(vec)) vec /= 2;
+    int64_t nvec = pd.total / vec;
+    unsigned grid = (unsigned)std::min<int64_t>(ceil_div(nvec, 256), grid_cap);
+    if (vec == 4) k_permute_rows<T, 4><<<grid, 256, 0, st>>>(src, dst, pd);
+    else if (vec == 2) k_permute_rows<T, 2><<<grid, 256, 0, st>>>(src, dst, pd);
+    else k_permute_rows<T, 1><<<grid, 256, 0, st>>>(src, dst, pd);
+    T10_LAUNCH_CHECK();
+    return T10_OK;
+  }
+  int ydim = -1;
+  for (int d = 0; d < last; ++d)
+    if (pd.sstride[d] == 1 && pd.shape[d] > 1) ydim = d;
+  if (ydim >= 0) {
+    int64_t tiles_x = ceil_div(pd.shape[last], 32), tiles_y = ceil_div(pd.shape[ydim], 32);
+    int64_t outer = pd.total / (pd.shape[last] * pd.shape[ydim]);
+    int64_t ntiles = tiles_x * tiles_y * outer;
+    unsigned grid = (unsigned)std::min<int64_t>(ntiles, grid_cap);
+    k_permute_tiled<T><<<grid, 256, 0, st>>>(src, dst, pd, ydim, tiles_x, tiles_y, ntiles);
+    T10_LAUNCH_CHECK();
+    return T10_OK;
+  }
+  unsigned grid = (unsigned)std::min<int64_t>(ceil_div(pd.total, 256), grid_cap);
+  k_permute_gather<T><<<grid, 256, 0, st>>>(src, dst, pd);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+}  // namespace t10
+
+using namespace t10;
+
+extern "C" int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntiles,
+                                   const int32_t* d_tiles, const int64_t* d_dst_sec,
+                                   const int32_t* d_RR, const int32_t* d_RC, const int32_t* d_CR,
+                                   const int32_t* d_CC, const int64_t* d_rowbase,
+                                   const int32_t* d_coloff, const int64_t* d_src_ket_map,
+                                   const int64_t* d_src_bra_map, t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ntiles == 0) return T10_OK;
+  const bool chk = d_src_ket_map != nullptr && d_src_bra_map != nullptr;
+  T10_REQUIRE(ntiles > 0, T10_ERR_INVALID, "ntiles < 0");
+  unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 8);
+#define T10_RL_LAUNCH(T, CHK)                                                                   \
+  k_relayout_blocks<T, CHK><<<grid, RL_THREADS, 0, st>>>(                                       \
+      (const T*)d_src, (T*)d_dst, ntiles, (const int4*)d_tiles, d_dst_sec, d_RR, d_RC, d_CR, d_CC, \
+      d_rowbase, d_coloff, d_src_ket_map, d_src_bra_map)
+  if (dtype == T10_F64) {
+    if (chk) T10_RL_LAUNCH(double, true); else T10_RL_LAUNCH(double, false);
+  } else if (dtype == T10_F32) {
+    if (chk) T10_RL_LAUNCH(float, true); else T10_RL_LAUNCH(float, false);
+  } else {
+    T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "relayout: dtype %d not supported", dtype);
+  }
+#undef T10_RL_LAUNCH
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+extern "C" int t10_permute_dense(int dtype, const void* d_src, void* d_dst, int rank,
+                                 const int64_t* h_shape, const int64_t* h_src_strides,
+                                 t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  T10_REQUIRE(rank >= 0 && rank <= T10_MAX_RANK, T10_ERR_INVALID, "rank %d outside [0,%d]", rank,
+              T10_MAX_RANK);
+  T10_REQUIRE(dtype == T10_F64 || dtype == T10_F32, T10_ERR_UNSUPPORTED, "permute: dtype %d", dtype);
+  // drop size-1 dims, merge dims that stay adjacent in the source
+  PermDesc pd;
+  pd.rank = 0;
+  pd.total = 1;
+  for (int d = 0; d < rank; ++d) {
+    T10_REQUIRE(h_shape[d] >= 0, T10_ERR_INVALID, "negative extent");
+    pd.total *= h_shape[d];
+    if (h_shape[d] == 1) continue;
+    if (pd.rank > 0 && pd.sstride[pd.rank - 1] == h_shape[d] * h_src_strides[d]) {
+      pd.shape[pd.rank - 1] *= h_shape[d];
+      pd.sstride[pd.rank - 1] = h_src_strides[d];
+    } else {
+      pd.shape[pd.rank] = h_shape[d];
+      pd.sstride[pd.rank] = h_src_strides[d];
+      ++pd.rank;
+    }
+  }
+  if (pd.total == 0) return T10_OK;
+  if (pd.rank == 0) {  // scalar / all-ones shape
+    pd.rank = 1;
+    pd.shape[0] = 1;
+    pd.sstride[0] = 1;
+  }
+  if (dtype == T10_F64) return launch_permute<double>((const double*)d_src, (double*)d_dst, pd, st);
+  return launch_permute<float>((const float*)d_src, (float*)d_dst, pd, st);
+}
+
+extern "C" int t10_diag_scale(int dtype, const void* d_a, const void* d_diag, void* d_out,
+                              int64_t rows, int64_t cols, int side, t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t n = rows * cols;
+  if (n == 0) return T10_OK;
+  unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
+  if (dtype == T10_F64)
+    k_diag_scale<double><<<grid, 256, 0, st>>>((const double*)d_a, (const double*)d_diag,
+                                                (double*)d_out, rows, cols, side);
+  else if (dtype == T10_F32)
+    k_diag_scale<float><<<grid, 256, 0, st>>>((const float*)d_a, (const float*)d_diag,
+                                               (float*)d_out, rows, cols, side);
+  else
+    T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "diag_scale: dtype %d", dtype);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}

@@ -1,0 +1,287 @@
+"""linalg (API of tor10/linalg.py).
+
+`Matmul` / `Chain_matmul` run on the family-3 GEMM kernel (reference: torch.matmul / chain_matmul,
+linalg.py:722-733, :806).  The decompositions stay on torch / cuSOLVER on the device, as the north
+star prescribes (`Svd_truncate` is timed separately by bench.py); they keep the reference's label
+and bond conventions.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from .Bond import Bond
+from .UniTensor import Contract, UniTensor, _dense_gemm
+
+
+def _new_label(a):
+    """Smallest negative label of `a` (0 if none): new internal bonds get tmp-1, tmp-2 (linalg.py:535-539)."""
+    neg = a.labels[a.labels < 0]
+    return 0 if len(neg) == 0 else int(np.min(neg))
+
+
+def _rank2(x, bonds=None, labels=None, is_diag=False):
+    if bonds is None:
+        n = x.shape[0]
+        bonds = [Bond(n), Bond(n)] if is_diag else [Bond(x.shape[0]), Bond(x.shape[1])]
+    t = UniTensor(bonds=bonds, rowrank=1, labels=labels, check=False, is_diag=is_diag)
+    t._mac(torch_tensor=x)
+    return t
+
+
+def _scalar(x):
+    t = UniTensor(bonds=[], labels=[], rowrank=0, check=False)
+    t._mac(torch_tensor=x)
+    return t
+
+
+def Hosvd(a, order, bonds_group, by_label=False, core=True):
+    """linalg.py:6-138 (dense tensors): factors U_g of each bond group and, optionally, the core."""
+    if not isinstance(a, UniTensor):
+        raise TypeError("Hosvd(UniTensor,*args)", "[ERROR] the input should be a UniTensor")
+    if not (isinstance(bonds_group, list) or isinstance(bonds_group, np.ndarray)):
+        raise TypeError("Hosvd(UniTensor,order,bonds_group,*args)",
+                        "[ERROR] the bonds_group should be a python list or 1d numpy array")
+    if not (isinstance(order, list) or isinstance(order, np.ndarray)):
+        raise TypeError("Hosvd(UniTensor,order,bonds_group,*args)",
+                        "[ERROR] the order should be a python list or 1d numpy array")
+    if len(order) != len(a.labels):
+        raise ValueError("Hosvd", "[ERROR] the size of order should be equal to the rank of input UniTensor.")
+    if len(a.labels) < 3:
+        raise Exception("Hosvd", "[ERROR], Hosvd can only perform on a UniTensor with rank > 2. For a rank-2 tensor, "
+                                 "using Svd() instead.")
+    if any(int(x) <= 0 for x in bonds_group):
+        raise ValueError("Hosvd", "[ERROR] bonds_group cannot have elements <=0")
+    if a.is_symm:
+        raise Exception("Hosvd can only operate on non-symmetry tensor")
+    if sum(int(x) for x in bonds_group) != len(a.labels):
+        raise ValueError("Hosvd", "[ERROR] bonds_group must cover all the bonds")
+    lbls = np.array(order, dtype=np.int64) if by_label else a.labels[np.array(order, dtype=np.int64)]
+    work = copy.deepcopy(a)
+    work.Permute(lbls, by_label=True)
+    start = int(np.min(a.labels))
+    start = start - 1 if start <= 0 else -1
+    factors, pos = [], 0
+    x = UniTensor._contiguous_dense(work._dense)
+    for g in bonds_group:
+        g = int(g)
+        front = list(range(pos, pos + g))
+        rest = [i for i in range(x.dim()) if i not in front]
+        mat = UniTensor._contiguous_dense(x.permute(front + rest)).reshape(
+            int(np.prod([x.shape[i] for i in front])), -1)
+        u, _, _ = torch.linalg.svd(mat, full_matrices=False)
+        f = UniTensor(bonds=[Bond(int(x.shape[i])) for i in front] + [Bond(u.shape[-1])],
+                      labels=list(lbls[pos:pos + g]) + [start], rowrank=g, check=False)
+        f._mac(torch_tensor=u.reshape([int(x.shape[i]) for i in front] + [u.shape[-1]]))
+        factors.append(f)
+        start -= 1
+        pos += g
+    if not core:
+        return factors
+    out = work
+    for f in factors:
+        out = Contract(out, f)
+    return factors, out
+
+
+def Abs(a):
+    if not isinstance(a, UniTensor):
+        raise TypeError("Abs(UniTensor)", "[ERROR] the input should be a UniTensor")
+    if a.is_symm:
+        return a._like(torch.abs(a._arena_tensor()))
+    return a._like(torch.abs(a._dense))
+
+
+def Mean(a):
+    if not isinstance(a, UniTensor):
+        raise TypeError("Mean(UniTensor)", "[ERROR] the input should be a UniTensor")
+    if a.is_symm:
+        raise Exception("Mean(UniTensor)", "[ERROR] cannot get mean for a symmetry tensor. GetBlock first")
+    return _scalar(torch.mean(a._dense))
+
+
+def Otimes(a, b):
+    """Kronecker product of two rank-2 untagged tensors (linalg.py:200-256)."""
+    if not (isinstance(a, UniTensor) and isinstance(b, UniTensor)):
+        raise TypeError("Otimes", "[ERROR], Otimes only accept UniTensor as arguments.")
+    if not (len(a.labels) == 2 and len(b.labels) == 2):
+        raise TypeError("Otimes", "[ERROR], Otimes only accept rank-2 UniTensors as arguments.")
+    if a.braket is not None or b.braket is not None:
+        raise TypeError("linalg.Otimes", "Otimes can only accept untagged tensor.")
+    if a.is_diag and b.is_diag:
+        return _rank2(torch.outer(a._dense, b._dense).reshape(-1), is_diag=True)
+    ta = torch.diag(a._dense) if a.is_diag else a._dense
+    tb = torch.diag(b._dense) if b.is_diag else b._dense
+    out = torch.tensordot(ta, tb, dims=0).permute(0, 2, 1, 3).reshape(ta.shape[0] * tb.shape[0], -1)
+    return _rank2(out)
+
+
+def ExpH(a):
+    """exp of a Hermitian rank-2 tensor via eigh (linalg.py:260-319; torch.symeig no longer exists)."""
+    if not isinstance(a, UniTensor):
+        raise Exception("ExpH(UniTensor)", "[ERROR] ExpH can only accept UniTensor")
+    if a.is_symm:
+        raise Exception("ExpH(a)", "don't support symm tensor. GetBlock first.")
+    if a.braket is not None:
+        raise Exception("ExpH(a)", "can only accept [untagged] type UniTensor")
+    if a.is_diag:
+        return _rank2(torch.exp(a._dense), bonds=a.bonds, labels=a.labels, is_diag=True)
+    if len(a.labels) != 2 or a.rowrank != 1:
+        raise Exception("ExpH(a)", "a should be rank-2 tensor with 1 inbond 1 outbond")
+    s, u = torch.linalg.eigh(a._dense, UPLO="U")
+    s = torch.exp(s)
+    return _rank2(torch.matmul(u * s, u.transpose(0, 1)), bonds=a.bonds, labels=a.labels)
+
+
+def _check_rank2(a, who, allow_diag=False):
+    if a.is_symm:
+        raise Exception("%s(a)" % who, "[Abort] %s curretly don't support symm tensor." % who)
+    if a.is_diag and not allow_diag:
+        raise Exception("%s(a)" % who, "[Abort] %s currently don't support diagonal tensor." % who)
+    if a.braket is not None:
+        raise Exception("%s(a)" % who, "can only accept UniTensor[regular] (untagged)")
+    if len(a.labels) != 2 or a.rowrank != 1:
+        raise Exception("%s(a)" % who, "should be a UniTensor with 1 in-bond, 1 out-bond")
+
+
+def Qr(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Qr(UniTensor)", "[ERROR] Qr can only accept UniTensor")
+    _check_rank2(a, "Qr")
+    q, r = torch.linalg.qr(a._dense)
+    tmp = _new_label(a)
+    tq = _rank2(q, labels=[a.labels[0], tmp - 1])
+    tr = _rank2(r, labels=[tq.labels[1], a.labels[1]])
+    return tq, tr
+
+
+def Qdr(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Qdr(UniTensor)", "[ERROR] Qdr can only accept UniTensor")
+    _check_rank2(a, "Qdr")
+    q, r = torch.linalg.qr(a._dense)
+    d = r.diag()
+    r = (r.t() / d).t()
+    tmp = _new_label(a)
+    tq = _rank2(q, labels=[a.labels[0], tmp - 1])
+    td = _rank2(d, labels=[tmp - 1, tmp - 2], is_diag=True)
+    tr = _rank2(r, labels=[td.labels[1], a.labels[1]])
+    return tq, td, tr
+
+
+def _svd(a, keepdim, who):
+    _check_rank2(a, who)
+    # torch.svd(some=True) of the reference == linalg.svd(full_matrices=False) with V = Vh^T
+    u, s, vh = torch.linalg.svd(a._dense, full_matrices=False)
+    tmp = _new_label(a)
+    if keepdim is not None:
+        if keepdim < 0 or keepdim > len(s):
+            raise ValueError("Svd_truncate", "[ERROR] the keepdim=%d is invalid, must larger than 0 and smaller than "
+                                             "the total number of eigenvalues." % keepdim)
+        u, s, vh = u[:, :keepdim], s[:keepdim], vh[:keepdim, :]
+    tu = _rank2(u, labels=[a.labels[0], tmp - 1])
+    tv = _rank2(vh, labels=[tmp - 2, a.labels[1]])
+    ts = UniTensor(bonds=[tu.bonds[1], tv.bonds[0]], labels=[tu.labels[1], tv.labels[0]], rowrank=1, check=False,
+                   is_diag=True)
+    ts._mac(torch_tensor=s)
+    return tu, ts, tv
+
+
+def Svd(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Svd(UniTensor)", "[ERROR] Svd can only accept UniTensor")
+    return _svd(a, None, "svd")
+
+
+def Svd_truncate(a, keepdim=None):
+    if not isinstance(a, UniTensor):
+        raise Exception("Svd_truncate(UniTensor,int)", "[ERROR] Svd_truncate can only accept UniTensor")
+    return _svd(a, keepdim, "svd")
+
+
+def Matmul(a, b):
+    """linalg.py:680-737.  diag x diag: the reference returns the DOT PRODUCT of the two diagonals flagged
+    is_diag (torch.matmul of two 1-D tensors, :717-722) -- a bug; the element-wise product (the diagonal
+    of the matrix product) is returned here instead."""
+    if not (isinstance(a, UniTensor) and isinstance(b, UniTensor)):
+        raise TypeError("_Matmul(a,b)", "[ERROR] _Matmul can only accept UniTensors for both a & b")
+    if a.is_symm or b.is_symm:
+        raise Exception("Matmul(a,b)", "[Abort] Matmul cannot operate on sym TN.")
+    if a.braket is not None or b.braket is not None:
+        raise Exception("Matmul(a,b)", "Matmul can only accept two regular Tensors")
+    if not (len(a.labels) == 2 and len(b.labels) == 2 and a.rowrank == 1 and b.rowrank == 1):
+        raise Exception("Matmul(a,b)", "Matmul can only accept two UniTensor with each has 1 inbond and 1 outbond")
+    bonds = [a.bonds[0], b.bonds[1]]
+    if a.is_diag and b.is_diag:
+        return _rank2(a._dense * b._dense, bonds=bonds, is_diag=True)
+    if a.is_diag:
+        return _rank2(_scale(b._dense, a._dense, side=0), bonds=bonds)
+    if b.is_diag:
+        return _rank2(_scale(a._dense, b._dense, side=1), bonds=bonds)
+    return _rank2(_dense_gemm(UniTensor._contiguous_dense(a._dense), UniTensor._contiguous_dense(b._dense)),
+                  bonds=bonds)
+
+
+def _scale(mat, diag, side):
+    """diag(d) @ mat (side 0) or mat @ diag(d) (side 1): family-2 scaling kernel, no densified diagonal."""
+    from . import _lib
+    mat = UniTensor._contiguous_dense(mat)
+    _lib.require_cuda_tensor(mat, "Matmul")
+    out = torch.empty_like(mat)
+    with torch.cuda.device(mat.device):
+        _lib.check(_lib.load().t10_diag_scale(_lib.dtype_code(mat.dtype), mat.data_ptr(), diag.contiguous().data_ptr(),
+                                              out.data_ptr(), mat.shape[0], mat.shape[1], side, _lib.stream_ptr()))
+    return out
+
+
+def Chain_matmul(*args):
+    """linalg.py:740-810: left-to-right chain on the GEMM kernel."""
+    if not all(isinstance(x, UniTensor) for x in args):
+        raise TypeError("_Chain_matmul(*args)", "[ERROR] _Chain_matmul can only accept UniTensors for all elements in "
+                                                "args")
+    if any(x.is_symm for x in args):
+        raise Exception("Chain_matmul(*args)", "[Abort] Chain multiplication for symm tensor(s) are under developing.")
+    if not all(len(x.labels) == 2 and x.rowrank == 1 for x in args):
+        raise Exception("Chain_matmul(*args)", "Chain mult should have all UniTensor have 1 inbond 1 outbond")
+    out = args[0]
+    for nxt in args[1:]:
+        out = Matmul(out, nxt)
+    res = UniTensor(bonds=[args[0].bonds[0], args[-1].bonds[1]], rowrank=1, check=False)
+    res._mac(torch_tensor=torch.diag(out._dense) if out.is_diag else out._dense)
+    return res
+
+
+def Inverse(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Inverse(UniTensor)", "[ERROR] Inverse can only accept UniTensor")
+    if a.is_symm:
+        raise TypeError("Inverse", "[ERROR] cannot inverse a symmetry tensor")
+    if a.braket is not None:
+        raise TypeError("Inverse", "[ERROR] inverse can only accept untagged UniTensor[regular]")
+    if a.rowrank != 1 or len(a.labels) != 2:
+        raise Exception("Inverse", "[ERROR] inverse should have UniTensor with rowrank=1")
+    if a.is_diag:
+        return _rank2(a._dense ** -1, bonds=a.bonds, labels=a.labels, is_diag=True)
+    return _rank2(torch.inverse(a._dense), bonds=a.bonds, labels=a.labels)
+
+
+def Det(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Det(UniTensor)", "[ERROR] Det can only accept UniTensor")
+    if a.is_symm:
+        raise Exception("Det", "[ERROR] cannot operate deteminant on a symmetry tensor")
+    if a.braket is not None:
+        raise Exception("Det", "[ERROR] det can only operate on untagged UniTensor[regular]")
+    if a.rowrank != 1 or len(a.labels) != 2:
+        raise Exception("Det", "[ERROR] det should have a rank-2 UniTensor with rowrank=1")
+    return _scalar(torch.prod(a._dense) if a.is_diag else torch.det(a._dense))
+
+
+def Norm(a):
+    if not isinstance(a, UniTensor):
+        raise Exception("Norm(UniTensor)", "[ERROR] Norm can only accept UniTensor")
+    if a.is_symm:
+        raise Exception("Norm", "[ERROR] cannot operate Norm on a symmetry tensor")
+    if a.braket is not None:
+        raise Exception("Norm", "[ERROR] Norm can only operate on untagged UniTensor")
+    return _scalar(torch.norm(a._dense))
