@@ -56,7 +56,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -124,7 +124,7 @@ def cpu_port_run(chi, budget_s, max_reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chi", type=int, default=4096)

@@ -113,20 +113,34 @@ int t10_relayout_tables(int64_t n, int nb, const int64_t* h_dims, const int64_t*
 
 /* Block-sparse strided permute (gather form).  For every destination sector s, row r,
  * column c:   dst[off_s + r*ld_s + c] = src[rowbase[RR[ks+r]+CR[bs+c]] + coloff[RC[ks+r]+CC[bs+c]]]
- * (0 where the source element is not stored).  d_tiles [ntiles,4] = {sector, r0, c0, 0};
- * d_dst_sec [nsec,8] = {rows, cols, ket_start, bra_start, dst_off, dst_ld, 0, 0}.
- * A tile covers T10_RELAYOUT_TR rows x T10_RELAYOUT_TC columns.
+ * (0 where the source element is not stored).  The destination is cut into tiles of at most
+ * T10_RELAYOUT_TR rows x T10_RELAYOUT_TC columns; a tile record is self-contained:
+ *   dst   = off_s + r0*ld_s + c0   element offset of the tile's first element in d_dst
+ *   rbase = ks + r0, cbase = bs + c0   first entries of the tile in RR/RC and CR/CC
+ *   nr, nc = rows / columns of the tile, dld = ld_s
  * d_src_ket_map / d_src_bra_map (the source layout's [R,2] / [C,2] maps) may be NULL; when
  * given, an element is copied only if its source row and column lie in the SAME sector
  * (needed for Zn layouts whose sign-flipped single-bond spaces lose sectors, quirk Q3).   */
 #define T10_RELAYOUT_TR 32
 #define T10_RELAYOUT_TC 128
+typedef struct t10_relayout_tile {
+  int64_t dst;
+  int32_t rbase, cbase, nr, nc, dld, pad;
+} t10_relayout_tile;
 int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntiles,
-                        const int32_t* d_tiles, const int64_t* d_dst_sec,
-                        const int32_t* d_RR, const int32_t* d_RC, const int32_t* d_CR,
-                        const int32_t* d_CC, const int64_t* d_rowbase, const int32_t* d_coloff,
-                        const int64_t* d_src_ket_map, const int64_t* d_src_bra_map,
-                        t10_stream_t stream);
+                        const t10_relayout_tile* d_tiles, const int32_t* d_RR, const int32_t* d_RC,
+                        const int32_t* d_CR, const int32_t* d_CC, const int64_t* d_rowbase,
+                        const int32_t* d_coloff, const int64_t* d_src_ket_map,
+                        const int64_t* d_src_bra_map, int32_t* d_emit_index, t10_stream_t stream);
+
+/* Replay of a relayout through its element index.  t10_relayout_blocks with d_emit_index != NULL
+ * writes, instead of data, the source element index of every destination element it covers into
+ * d_emit_index (same addressing as d_dst; -1 where the source is not stored).  t10_relayout_index then
+ * performs dst[i] = src[index[i]] for i < n (index -1: dst[i] = 0; -2: dst[i] untouched).  n even,
+ * d_dst 16-byte aligned.  Costs 4 B of plan memory and 4 B of extra traffic per element, and cuts
+ * the dependent-load chain of the relayout from four loads to two.                           */
+int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_index,
+                       t10_stream_t stream);
 
 /* Dense strided permute: dst (contiguous, shape = h_shape) [i0..i_{r-1}] =
  * src[sum_k i_k * h_src_strides[k]]  (strides in elements).                            */
@@ -147,21 +161,34 @@ typedef struct t10_gemm_problem {
   int32_t lda, ldb, ldc;
 } t10_gemm_problem;
 
-/* Tile decomposition used by t10_ggemm for `tile_cfg` (0: 64x64, 1: 128x128, 2: 128x64).
- * Fills h_tiles [cap,4] = {problem, m0, n0, 0} in launch order (heaviest first) and
- * returns the tile count through *ntiles (call with h_tiles = NULL to size).           */
+/* Tile decomposition used by t10_ggemm for `tile_cfg`:
+ *   0: 64x64xBK16, 4 stages   1: 128x128   2: 128x64   3: 64x64xBK16, 3 stages (3 CTAs/SM)
+ *   4: 64x64xBK32, 3 stages   5: 64x64xBK32, 2 stages   100: SIMT cross-check kernel (tests)
+ * t10_ggemm_slots: number of co-resident CTAs of that kernel on the current device (needs CUDA).
+ * t10_ggemm_plan_tiles (host only): fills h_tiles [cap,4] = {problem, m0, n0, 0}; call with
+ * h_tiles = NULL to size.  With nslots > 0 the tiles are assigned to `nslots` CTA slots by LPT on a
+ * DMMA-count cost model and stored slot-major, h_slot_start [nslots+1] delimiting each slot;
+ * with nslots = 0 they are listed heaviest first for a grid-strided walk.                  */
 int t10_ggemm_tile_shape(int tile_cfg, int* bm, int* bn);
-int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_problem* h_prob,
-                         int64_t cap, int32_t* h_tiles, int64_t* ntiles);
+int t10_ggemm_slots(int dtype, int tile_cfg, int* nslots);
+int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_problem* h_prob, int64_t nslots,
+                         int64_t cap, int32_t* h_tiles, int32_t* h_slot_start, int64_t* ntiles);
 
-/* Grouped GEMM over the matched sectors: one persistent launch.                        */
+/* Grouped GEMM over the matched sectors: one persistent launch.  Tile schedule:
+ *   d_sched != NULL      dynamic: CTAs pull tiles from the heaviest-first list (built with nslots = 0)
+ *                        through d_sched[0]; d_sched is a zero-initialised int32[2] owned by the caller
+ *                        and private to one stream (the kernel resets it before it exits);
+ *   d_slot_start != NULL static LPT slots (grid = nslots);
+ *   neither              grid-strided walk (grid = min(ntiles, resident CTAs)).            */
 int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d_C,
               int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
-              const int32_t* d_tiles, t10_stream_t stream);
+              const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
+              int32_t* d_sched, t10_stream_t stream);
 
-/* Peak-rate probes used by bench.py for the roofline denominators (register-resident
- * DMMA / DFMA loops; returns achieved TFLOP/s through *tflops).                        */
-int t10_probe_f64_peak(int use_dmma, int iters, double* tflops, t10_stream_t stream);
+/* Peak-rate probes used by bench.py for the roofline denominators (register-resident loops;
+ * mode 1: DMMA, 0: DFMA, 2: DMMA and DFMA warps side by side -- measured 37.0 / 36.5 / 36.8 TF on
+ * B200: the two share one FP64 datapath).  Returns achieved TFLOP/s through *tflops.     */
+int t10_probe_f64_peak(int mode, int iters, double* tflops, t10_stream_t stream);
 
 #ifdef __cplusplus
 }

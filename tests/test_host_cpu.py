@@ -50,13 +50,21 @@ def test_tile_planner_host_side(T):
     for cfg, (bm, bn) in {0: (64, 64), 1: (128, 128), 2: (128, 64)}.items():
         n = ctypes.c_int64(0)
         lib = T._lib.load()
-        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), 0, None, ctypes.byref(n)) == 0
+        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), 0, 0, None, None, ctypes.byref(n)) == 0
         tiles = np.zeros((n.value, 4), dtype=np.int32)
-        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), n.value, T._lib.np_ptr(tiles), ctypes.byref(n)) == 0
+        assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), 0, n.value, T._lib.np_ptr(tiles), None,
+                                        ctypes.byref(n)) == 0
         want = -(-130 // bm) * -(-70 // bn) + 1
         assert n.value == want
-        assert tiles[0, 0] == 1                     # k=500 problem first
         assert set(tiles[:, 0].tolist()) == {0, 1}  # empty problem produces no tile
+        # LPT slot table: every tile exactly once, slot-major, slots cover [0, ntiles)
+        for nslots in (1, 2, 5):
+            t2 = np.zeros((n.value, 4), dtype=np.int32)
+            ss = np.zeros(nslots + 1, dtype=np.int32)
+            assert lib.t10_ggemm_plan_tiles(cfg, 3, T._lib.np_ptr(prob), nslots, n.value, T._lib.np_ptr(t2),
+                                            T._lib.np_ptr(ss), ctypes.byref(n)) == 0
+            assert ss[0] == 0 and ss[-1] == n.value and (np.diff(ss) >= 0).all()
+            assert sorted(map(tuple, t2.tolist())) == sorted(map(tuple, tiles.tolist()))
         b0, b1 = ctypes.c_int(0), ctypes.c_int(0)
         assert lib.t10_ggemm_tile_shape(cfg, ctypes.byref(b0), ctypes.byref(b1)) == 0 and (b0.value, b1.value) == (bm, bn)
 

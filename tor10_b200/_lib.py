@@ -43,6 +43,9 @@ GEMM_PROBLEM_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("c_off", "<i
                                ("m", "<i4"), ("n", "<i4"), ("k", "<i4"),
                                ("lda", "<i4"), ("ldb", "<i4"), ("ldc", "<i4")])
 assert GEMM_PROBLEM_DTYPE.itemsize == C.sizeof(GemmProblem) == 48
+RELAYOUT_TILE_DTYPE = np.dtype([("dst", "<i8"), ("rbase", "<i4"), ("cbase", "<i4"), ("nr", "<i4"), ("nc", "<i4"),
+                                ("dld", "<i4"), ("pad", "<i4")])
+assert RELAYOUT_TILE_DTYPE.itemsize == 32
 
 _p = C.c_void_p
 _i = C.c_int
@@ -58,11 +61,13 @@ SIGNATURES = {
     "t10_unravel": [_l, _i, _p, _p, _p, _p],
     "t10_relayout_tables": [_l, _i, _p, _p, _p, _p, _p, _p, _p],
     "t10_relayout_blocks": [_i, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "t10_relayout_index": [_i, _p, _p, _l, _p, _p],
     "t10_permute_dense": [_i, _p, _p, _i, _p, _p, _p],
     "t10_diag_scale": [_i, _p, _p, _p, _l, _l, _i, _p],
     "t10_ggemm_tile_shape": [_i, _p, _p],
-    "t10_ggemm_plan_tiles": [_i, _l, _p, _l, _p, _p],
-    "t10_ggemm": [_i, _i, _p, _p, _p, _l, _p, _l, _p, _p],
+    "t10_ggemm_slots": [_i, _i, _p],
+    "t10_ggemm_plan_tiles": [_i, _l, _p, _l, _l, _p, _p, _p],
+    "t10_ggemm": [_i, _i, _p, _p, _p, _l, _p, _l, _p, _l, _p, _p, _p],
     "t10_probe_f64_peak": [_i, _i, _p, _p],
 }
 

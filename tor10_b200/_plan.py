@@ -10,6 +10,7 @@ The reference recomputes all of this with numpy on every call (3 block-map build
 an O(nsec^2) sector search per Contract).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -169,7 +170,7 @@ class PackedLayout:
 
     @staticmethod
     def native(L):
-        return PackedLayout(L.arena_off, L.cols, L.arena_elems + ARENA_ALIGN)
+        return PackedLayout(L.arena_off, L.cols, L.arena_elems + ARENA_ALIGN)   # multiple of 16
 
     @staticmethod
     def padded(L):
@@ -215,35 +216,63 @@ class RelayoutPlan:
             check(lib.t10_relayout_tables(L.n_bra, rank - rr, np_ptr(i64(L.dims[rr:])), np_ptr(i64(srow[rr:])),
                                           np_ptr(i64(scol[rr:])), L.d_bra_idx.data_ptr(), self.CR.data_ptr(),
                                           self.CC.data_ptr(), st))
-        sec = np.zeros((L.nsec, 8), dtype=np.int64)
-        sec[:, 0], sec[:, 1], sec[:, 2], sec[:, 3] = L.rows, L.cols, L.ket_start, L.bra_start
-        sec[:, 4], sec[:, 5] = packed.off, packed.ld
-        self.d_sec = torch.from_numpy(sec).to(dev)
         tiles = []
         for s in (range(L.nsec) if sectors is None else sectors):
             r, c = int(L.rows[s]), int(L.cols[s])
             nr, nc = -(-r // RELAYOUT_TR), -(-c // RELAYOUT_TC)
             if nr * nc == 0:
                 continue
-            t = np.zeros((nr, nc, 4), dtype=np.int32)
-            t[:, :, 0] = s
-            t[:, :, 1] = (np.arange(nr, dtype=np.int32) * RELAYOUT_TR)[:, None]
-            t[:, :, 2] = (np.arange(nc, dtype=np.int32) * RELAYOUT_TC)[None, :]
-            tiles.append(t.reshape(-1, 4))
-        tiles = np.concatenate(tiles) if tiles else np.zeros((0, 4), dtype=np.int32)
+            r0 = (np.arange(nr, dtype=np.int64) * RELAYOUT_TR)[:, None]
+            c0 = (np.arange(nc, dtype=np.int64) * RELAYOUT_TC)[None, :]
+            t = np.zeros((nr, nc), dtype=_lib.RELAYOUT_TILE_DTYPE)
+            off, ld = int(packed.off[s]), int(packed.ld[s])
+            t["dst"] = off + r0 * ld + c0
+            t["rbase"] = int(L.ket_start[s]) + r0
+            t["cbase"] = int(L.bra_start[s]) + c0
+            t["nr"] = np.minimum(RELAYOUT_TR, r - r0)
+            t["nc"] = np.minimum(RELAYOUT_TC, c - c0)
+            t["dld"] = ld
+            tiles.append(t.reshape(-1))
+        tiles = np.concatenate(tiles) if tiles else np.zeros(0, dtype=_lib.RELAYOUT_TILE_DTYPE)
         self.ntiles = len(tiles)
-        self.d_tiles = torch.from_numpy(tiles).to(dev)
+        self.d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(dev) if self.ntiles else \
+            torch.zeros(32, dtype=torch.uint8, device=dev)
+        self.d_index = None
+        self.index_n = 0
+        self.use_index = (os.environ.get("TOR10_RELAYOUT_INDEX", "1") == "1"
+                          and 4 * packed.size <= self.INDEX_BUDGET_BYTES)
         self.moved_elems = int(sum(int(L.rows[s]) * int(L.cols[s])
                                    for s in (range(L.nsec) if sectors is None else sectors)))
 
-    def run(self, src_arena, dst):
-        """dst must hold packed.size elements; padding/unmatched space is left untouched."""
+    INDEX_BUDGET_BYTES = int(os.environ.get("TOR10_RELAYOUT_INDEX_MB", "1024")) << 20
+
+    def _build_index(self):
+        """Element index of the relayout (plan time): the block kernel in EMIT mode."""
+        n = (self.packed.size + 1) // 2 * 2
+        self.index_n = n
+        self.d_index = torch.full((n,), -2, device=self.L.device, dtype=torch.int32)
         check(_lib.load().t10_relayout_blocks(
-            _lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(), self.ntiles,
-            self.d_tiles.data_ptr(), self.d_sec.data_ptr(), self.RR.data_ptr(), self.RC.data_ptr(),
+            _lib.T10_F64, None, None, self.ntiles, self.d_tiles.data_ptr(), self.RR.data_ptr(), self.RC.data_ptr(),
             self.CR.data_ptr(), self.CC.data_ptr(), self.M.d_rowbase.data_ptr(), self.M.d_coloff.data_ptr(),
             self.M.d_ket_map.data_ptr() if self.check else None, self.M.d_bra_map.data_ptr() if self.check else None,
-            _lib.stream_ptr()))
+            self.d_index.data_ptr(), _lib.stream_ptr()))
+
+    def run(self, src_arena, dst):
+        """dst must hold packed.size elements; padding/unmatched space is left untouched."""
+        if self.use_index and self.d_index is None and self.ntiles and src_arena.numel() < 2 ** 31:
+            with torch.cuda.device(self.L.device):
+                self._build_index()
+        if self.d_index is not None and dst.numel() >= self.index_n and dst.data_ptr() % 16 == 0:
+            check(_lib.load().t10_relayout_index(_lib.dtype_code(src_arena.dtype), src_arena.data_ptr(),
+                                                 dst.data_ptr(), self.index_n, self.d_index.data_ptr(),
+                                                 _lib.stream_ptr()))
+            return dst
+        check(_lib.load().t10_relayout_blocks(
+            _lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(), self.ntiles,
+            self.d_tiles.data_ptr(), self.RR.data_ptr(), self.RC.data_ptr(),
+            self.CR.data_ptr(), self.CC.data_ptr(), self.M.d_rowbase.data_ptr(), self.M.d_coloff.data_ptr(),
+            self.M.d_ket_map.data_ptr() if self.check else None, self.M.d_bra_map.data_ptr() if self.check else None,
+            None, _lib.stream_ptr()))
         return dst
 
 
@@ -268,18 +297,13 @@ def label_match(la, lb):
 
 
 def pick_tile_cfg(problems):
-    """64x64 tiles unless the group is dominated by large GEMMs that fill >= 2 waves of 128x128."""
-    import os
+    """Tile configuration of the FP64 grouped GEMM (see t10_ggemm_plan_tiles).  Measured on B200 at C3a
+    (42 ragged sectors, chi=4096): 64x64x16 tiles, 3 stages, 3 CTAs/SM with fragment-granular skipping of
+    ragged edges and static LPT slots is the fastest of the twelve variants in csrc/ggemm.cu (profiles/)."""
     forced = os.environ.get("TOR10_GGEMM_CFG")
     if forced is not None:
         return int(forced)
-    n128 = sum((-(-int(p["m"]) // 128)) * (-(-int(p["n"]) // 128)) for p in problems
-               if p["m"] >= 96 and p["n"] >= 96)
-    big = sum(int(p["m"]) * int(p["n"]) * int(p["k"]) for p in problems if p["m"] >= 96 and p["n"] >= 96)
-    tot = sum(int(p["m"]) * int(p["n"]) * int(p["k"]) for p in problems) or 1
-    if n128 >= 2 * 148 and big > 0.9 * tot:
-        return 1
-    return 0
+    return 3
 
 
 class GemmGroup:
@@ -293,14 +317,26 @@ class GemmGroup:
         if tile_cfg is None:
             tile_cfg = pick_tile_cfg(self.problems) if dtype == torch.float64 else 0
         self.tile_cfg = int(tile_cfg)
-        plan_cfg = 0 if self.tile_cfg == 100 else self.tile_cfg
+        # CTA slots of the persistent kernel (occupancy query: needs the device) -> LPT slot table
+        ns = C.c_int(0)
+        with torch.cuda.device(device):
+            check(lib.t10_ggemm_slots(self.dtype_code, self.tile_cfg, C.byref(ns)))
+        mode = os.environ.get("TOR10_GGEMM_SCHED", "slots")
+        f64k = dtype == torch.float64 and self.tile_cfg != 100
+        use_slots = f64k and (mode == "slots" or (mode == "dynamic" and self.tile_cfg >= 10))
+        self.d_sched = torch.zeros(2, dtype=torch.int32, device=device) \
+            if (f64k and mode == "dynamic" and self.tile_cfg < 10) else None
         nt = C.c_int64(0)
-        check(lib.t10_ggemm_plan_tiles(plan_cfg, self.nprob, np_ptr(self.problems), 0, None, C.byref(nt)))
-        tiles = np.zeros((max(nt.value, 1), 4), dtype=np.int32)
-        check(lib.t10_ggemm_plan_tiles(plan_cfg, self.nprob, np_ptr(self.problems), nt.value, np_ptr(tiles),
+        check(lib.t10_ggemm_plan_tiles(self.tile_cfg, self.nprob, np_ptr(self.problems), 0, 0, None, None,
                                        C.byref(nt)))
+        self.nslots = min(int(ns.value), max(int(nt.value), 1)) if use_slots else 0
+        tiles = np.zeros((max(nt.value, 1), 4), dtype=np.int32)
+        slots = np.zeros(self.nslots + 1, dtype=np.int32)
+        check(lib.t10_ggemm_plan_tiles(self.tile_cfg, self.nprob, np_ptr(self.problems), self.nslots, nt.value,
+                                       np_ptr(tiles), np_ptr(slots) if self.nslots else None, C.byref(nt)))
         self.ntiles = int(nt.value)
         self.d_tiles = torch.from_numpy(tiles).to(device)
+        self.d_slots = torch.from_numpy(slots).to(device) if self.nslots else None
         self.d_prob = torch.from_numpy(self.problems.view(np.uint8).reshape(-1)).to(device) if self.nprob else \
             torch.zeros(48, dtype=torch.uint8, device=device)
         self.flops = float(sum(2.0 * int(p["m"]) * int(p["n"]) * int(p["k"]) for p in self.problems))
@@ -310,6 +346,8 @@ class GemmGroup:
     def run(self, A, B, Cc):
         check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
                                     self.nprob, self.d_prob.data_ptr(), self.ntiles, self.d_tiles.data_ptr(),
+                                    self.nslots, self.d_slots.data_ptr() if self.nslots else None,
+                                    self.d_sched.data_ptr() if self.d_sched is not None else None,
                                     _lib.stream_ptr()))
 
 

@@ -249,18 +249,25 @@ __global__ void k_rank_hist(const int32_t* __restrict__ key, const int32_t* __re
   }
 }
 
-// thread per sector: exclusive scan down the segments, totals out
+// block per sector: exclusive scan down the segments (in place), totals out
 __global__ void k_rank_scan(int32_t* __restrict__ hist, int64_t nseg, int64_t nsec,
                             int64_t* __restrict__ totals) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsec) return;
-  int64_t run = 0;
-  for (int64_t g = 0; g < nseg; ++g) {
-    int32_t v = hist[g * nsec + s];
-    hist[g * nsec + s] = (int32_t)run;
-    run += v;
+  __shared__ int carry_s;
+  const int64_t s = blockIdx.x;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nseg; base += SCAN_THREADS) {
+    const int64_t g = base + threadIdx.x;
+    const int v = g < nseg ? hist[g * nsec + s] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, &total);
+    const int carry = carry_s;
+    if (g < nseg) hist[g * nsec + s] = ex + carry;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
   }
-  totals[s] = run;
+  if (threadIdx.x == 0) totals[s] = carry_s;
 }
 
 // sec_info [nsec,8] = {rows, cols, ket_start, bra_start, arena_off, 0, 0, 0}
@@ -543,8 +550,8 @@ extern "C" int t10_blockmap_build(int rank, int rowrank, int nsym, const int64_t
                                                                      nseg_in, nsec, hist_in);
   k_rank_hist<<<(unsigned)ceil_div(nseg_out * 32, 128), 128, 0, st>>>(key_out, sec_of_key, C, S_out,
                                                                       nseg_out, nsec, hist_out);
-  k_rank_scan<<<(unsigned)ceil_div(nsec, 128), 128, 0, st>>>(hist_in, nseg_in, nsec, tot_in);
-  k_rank_scan<<<(unsigned)ceil_div(nsec, 128), 128, 0, st>>>(hist_out, nseg_out, nsec, tot_out);
+  k_rank_scan<<<(unsigned)nsec, SCAN_THREADS, 0, st>>>(hist_in, nseg_in, nsec, tot_in);
+  k_rank_scan<<<(unsigned)nsec, SCAN_THREADS, 0, st>>>(hist_out, nseg_out, nsec, tot_out);
   k_sector_offsets<<<1, 32, 0, st>>>(tot_in, tot_out, nsec, d_sec_info, d_counts);
   T10_LAUNCH_CHECK();
   k_rank_write<<<(unsigned)ceil_div(nseg_in * 32, 128), 128, 0, st>>>(

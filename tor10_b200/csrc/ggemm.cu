@@ -44,9 +44,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // ------------------------------------------------------------------ FP64 DMMA ------
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int BK_ = 16>
 struct F64Cfg {
-  static constexpr int BM = BM_, BN = BN_, BK = 16, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WM = WM_, WN = WN_, STAGES = STAGES_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
   static constexpr int LDA = BK + 4;  // doubles; row stride = 8 banks mod 32 -> conflict-free LDS.64
@@ -95,19 +95,91 @@ __device__ __forceinline__ void load_stage_f64(double* As, double* Bs, const dou
   }
 }
 
-template <class Cfg, int MIN_CTAS>
+// Lean loader of the aligned fast path: pointers, clamped row/column offsets and shared-memory
+// destinations are set up once per tile; a k-step costs one LDGSTS.128 + one 64-bit add per chunk.
+// Rows beyond m / columns beyond n are CLAMPED to the last valid row / chunk instead of predicated:
+// they only feed accumulators that are never stored.  Only the K tail needs zero fill (it would
+// pollute valid outputs); that one step per tile goes through the predicated loader above.
+template <class Cfg>
+struct LeanLoader {
+  static constexpr int A_PASSES = (Cfg::BM * (Cfg::BK / 2)) / Cfg::THREADS;
+  static constexpr int B_PASSES = (Cfg::BK * (Cfg::BN / 2)) / Cfg::THREADS;
+  static constexpr int A_RPP = Cfg::THREADS / (Cfg::BK / 2);   // rows per pass
+  static constexpr int B_RPP = Cfg::THREADS / (Cfg::BN / 2);
+  static_assert((Cfg::BM * (Cfg::BK / 2)) % Cfg::THREADS == 0 && (Cfg::BK * (Cfg::BN / 2)) % Cfg::THREADS == 0, "");
+  const double* pa;
+  const double* pb;
+  int a_off[A_PASSES];   // element offsets of the pass rows (clamped) relative to pa
+  int b_off[B_PASSES];
+  int sa, sb;            // shared-memory element offsets of pass 0 inside a stage
+  int64_t b_kstep;       // BK * ldb
+
+  __device__ __forceinline__ void setup(const double* A, const double* B, int lda, int ldb, int m_rem, int n_rem) {
+    const int ar0 = threadIdx.x / (Cfg::BK / 2), akc = (threadIdx.x % (Cfg::BK / 2)) * 2;
+    const int br0 = threadIdx.x / (Cfg::BN / 2), bnc = (threadIdx.x % (Cfg::BN / 2)) * 2;
+    const int base_row = min(ar0, m_rem - 1);
+    pa = A + (int64_t)base_row * lda + akc;
+#pragma unroll
+    for (int i = 0; i < A_PASSES; ++i) a_off[i] = (min(ar0 + i * A_RPP, m_rem - 1) - base_row) * lda;
+    const int last_chunk = ((n_rem - 1) >> 1) << 1;
+    pb = B + (int64_t)br0 * ldb + min(bnc, last_chunk);
+#pragma unroll
+    for (int i = 0; i < B_PASSES; ++i) b_off[i] = i * B_RPP * ldb;
+    sa = ar0 * Cfg::LDA + akc;
+    sb = br0 * Cfg::LDB + bnc;
+    b_kstep = (int64_t)Cfg::BK * ldb;
+  }
+  // loads the k-step the pointers currently stand on, then advances them
+  __device__ __forceinline__ void issue(double* As, double* Bs) {
+#pragma unroll
+    for (int i = 0; i < A_PASSES; ++i) cp_async16(As + sa + i * A_RPP * Cfg::LDA, pa + a_off[i], 16);
+#pragma unroll
+    for (int i = 0; i < B_PASSES; ++i) cp_async16(Bs + sb + i * B_RPP * Cfg::LDB, pb + b_off[i], 16);
+    pa += Cfg::BK;
+    pb += b_kstep;
+  }
+};
+
+template <class Cfg, int MIN_CTAS, bool RAGGED>
 __global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
 k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
             double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
-            int64_t ntiles, const int4* __restrict__ tiles) {
+            int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start,
+            int32_t* __restrict__ sched) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ int s_next[2];
   double* As = smem;
   double* Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
 
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  // Tile schedule, one of
+  //   dynamic  (sched != NULL): CTAs pull the next tile of the heaviest-first list through an atomic
+  //            counter (list scheduling on measured, not modelled, tile times; the last CTA to leave
+  //            resets the two counters for the next launch on the stream)
+  //   slots    (slot_start != NULL): this CTA's LPT slot, tiles[slot_start[b] .. slot_start[b+1])
+  //   strided  grid-strided walk over the heaviest-first list
+  int64_t t_beg = blockIdx.x, t_end = ntiles, t_step = gridDim.x;
+  if (slot_start != nullptr) {
+    t_beg = slot_start[blockIdx.x];
+    t_end = slot_start[blockIdx.x + 1];
+    t_step = 1;
+  }
+  if (sched != nullptr) {
+    if (threadIdx.x == 0) s_next[0] = atomicAdd(&sched[0], 1);
+    __syncthreads();
+  }
+  for (int64_t t = t_beg, it = 0;; t += t_step, ++it) {
+    if (sched != nullptr) {
+      t = s_next[it & 1];
+      if (t >= ntiles) break;
+      // claim the tile after this one now: the atomic's latency hides behind this tile's k-loop; the
+      // barrier at the end of the iteration publishes it
+      if (threadIdx.x == 0) s_next[(it + 1) & 1] = atomicAdd(&sched[0], 1);
+    } else if (t >= t_end) {
+      break;
+    }
     const int4 tile = tiles[t];
     const t10_gemm_problem p = prob[tile.x];
     const int m0 = tile.y, n0 = tile.z;
@@ -117,6 +189,11 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
     const bool a16 = ((p.lda & 1) == 0) && ((p.a_off & 1) == 0) && (((uintptr_t)Abase & 15) == 0);
     const bool b16 = ((p.ldb & 1) == 0) && (((p.b_off + n0) & 1) == 0) && (((uintptr_t)Bbase & 15) == 0);
     const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
+    // k-steps served by the lean loader: all full ones when both operands are 16-byte aligned
+    const int KT_fast = (a16 && b16) ? p.k / Cfg::BK : 0;
+    const int mi_valid = max(0, min(Cfg::MI, (m_rem - wm0 + 7) >> 3));
+    const int ni_valid = max(0, min(Cfg::NI, (n_rem - wn0 + 7) >> 3));
+    const bool full = !RAGGED || ((mi_valid == Cfg::MI) && (ni_valid == Cfg::NI));
 
     double acc[Cfg::MI][Cfg::NI][2];
 #pragma unroll
@@ -124,46 +201,281 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
 #pragma unroll
       for (int j = 0; j < Cfg::NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    __syncthreads();  // all warps done reading the previous tile's stages
+    LeanLoader<Cfg> ld;
+    ld.setup(A, B, p.lda, p.ldb, m_rem, n_rem);
+    auto issue_stage = [&](int kt) {  // kt is issued in increasing order, so the lean pointers stay in step
+      double* as_ = As + (kt % Cfg::STAGES) * Cfg::A_STAGE;
+      double* bs_ = Bs + (kt % Cfg::STAGES) * Cfg::B_STAGE;
+      if (kt < KT_fast)
+        ld.issue(as_, bs_);
+      else
+        load_stage_f64<Cfg>(as_, bs_, A + kt * Cfg::BK, B + (int64_t)kt * Cfg::BK * p.ldb, p.lda, p.ldb, m_rem,
+                            n_rem, p.k - kt * Cfg::BK, a16, b16);
+    };
+
 #pragma unroll
     for (int s = 0; s < Cfg::STAGES - 1; ++s) {
-      if (s < KT)
-        load_stage_f64<Cfg>(As + s * Cfg::A_STAGE, Bs + s * Cfg::B_STAGE, A + s * Cfg::BK,
-                            B + (int64_t)s * Cfg::BK * p.ldb, p.lda, p.ldb, m_rem, n_rem,
-                            p.k - s * Cfg::BK, a16, b16);
+      if (s < KT) issue_stage(s);
       cp_async_commit();
     }
     for (int kt = 0; kt < KT; ++kt) {
       cp_async_wait<Cfg::STAGES - 2>();
       __syncthreads();
-      {
-        const int nk = kt + Cfg::STAGES - 1;
-        if (nk < KT) {
-          const int slot = nk % Cfg::STAGES;
-          load_stage_f64<Cfg>(As + slot * Cfg::A_STAGE, Bs + slot * Cfg::B_STAGE, A + nk * Cfg::BK,
-                              B + (int64_t)nk * Cfg::BK * p.ldb, p.lda, p.ldb, m_rem, n_rem,
-                              p.k - nk * Cfg::BK, a16, b16);
-        }
-        cp_async_commit();
-      }
+      if (kt + Cfg::STAGES - 1 < KT) issue_stage(kt + Cfg::STAGES - 1);
+      cp_async_commit();
       const double* as = As + (kt % Cfg::STAGES) * Cfg::A_STAGE + (wm0 + g) * Cfg::LDA + tig;
       const double* bs = Bs + (kt % Cfg::STAGES) * Cfg::B_STAGE + tig * Cfg::LDB + wn0 + g;
+      if (full) {
 #pragma unroll
-      for (int kk = 0; kk < Cfg::BK; kk += 4) {
-        double af[Cfg::MI], bf[Cfg::NI];
+        for (int kk = 0; kk < Cfg::BK; kk += 4) {
+          double af[Cfg::MI], bf[Cfg::NI];
 #pragma unroll
-        for (int i = 0; i < Cfg::MI; ++i) af[i] = as[i * 8 * Cfg::LDA + kk];
+          for (int i = 0; i < Cfg::MI; ++i) af[i] = as[i * 8 * Cfg::LDA + kk];
 #pragma unroll
-        for (int j = 0; j < Cfg::NI; ++j) bf[j] = bs[kk * Cfg::LDB + j * 8];
+          for (int j = 0; j < Cfg::NI; ++j) bf[j] = bs[kk * Cfg::LDB + j * 8];
 #pragma unroll
-        for (int i = 0; i < Cfg::MI; ++i)
+          for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
-          for (int j = 0; j < Cfg::NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int j = 0; j < Cfg::NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      } else if (mi_valid > 0 && ni_valid > 0) {
+        // ragged tile: 8x8 fragments that lie entirely outside the sector are skipped (warp-uniform)
+#pragma unroll
+        for (int kk = 0; kk < Cfg::BK; kk += 4) {
+          double af[Cfg::MI], bf[Cfg::NI];
+#pragma unroll
+          for (int i = 0; i < Cfg::MI; ++i) af[i] = as[i * 8 * Cfg::LDA + kk];
+#pragma unroll
+          for (int j = 0; j < Cfg::NI; ++j) bf[j] = bs[kk * Cfg::LDB + j * 8];
+#pragma unroll
+          for (int i = 0; i < Cfg::MI; ++i) {
+            if (i < mi_valid) {
+#pragma unroll
+              for (int j = 0; j < Cfg::NI; ++j)
+                if (j < ni_valid) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+          }
+        }
       }
     }
     cp_async_wait<0>();
 
     // epilogue: lane holds C[row g][cols 2*tig, 2*tig+1] of every 8x8 fragment
+    double* C = Cbase + p.c_off;
+    const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; ++i) {
+      const int r = m0 + wm0 + i * 8 + g;
+      if (r >= p.m) continue;
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; ++j) {
+        const int c = n0 + wn0 + j * 8 + 2 * tig;
+        double* o = C + (int64_t)r * p.ldc + c;
+        if (c + 1 < p.n) {
+          if (c16) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
+          else { o[0] = acc[i][j][0]; o[1] = acc[i][j][1]; }
+        } else if (c < p.n) {
+          o[0] = acc[i][j][0];
+        }
+      }
+    }
+    __syncthreads();  // stages free for the next tile; next tile index visible
+  }
+  if (sched != nullptr && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ FP64 DMMA, warp-specialised
+// One producer warp issues every cp.async of the CTA (per-lane row pointers set up once per tile, three
+// instructions per 16-byte chunk) and signals "stage full" through an mbarrier
+// (cp.async.mbarrier.arrive.noinc); the consumer warps run nothing but LDS.64 + DMMA and hand stages
+// back through an "empty" mbarrier.  No __syncthreads in the main loop, the pipeline state runs on
+// across tile boundaries (the producer prefetches the next tile while the consumers drain the current
+// one), and ragged tiles run a compute body specialised on the number of valid 8x8 fragments.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
+template <class Cfg, int MI_V, int NI_V>
+__device__ __forceinline__ void ws_compute(const double* __restrict__ as, const double* __restrict__ bs,
+                                           double (&acc)[Cfg::MI][Cfg::NI][2]) {
+#pragma unroll
+  for (int kk = 0; kk < Cfg::BK; kk += 4) {
+    double af[MI_V], bf[NI_V];
+#pragma unroll
+    for (int i = 0; i < MI_V; ++i) af[i] = as[i * 8 * Cfg::LDA + kk];
+#pragma unroll
+    for (int j = 0; j < NI_V; ++j) bf[j] = bs[kk * Cfg::LDB + j * 8];
+#pragma unroll
+    for (int i = 0; i < MI_V; ++i)
+#pragma unroll
+      for (int j = 0; j < NI_V; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+
+template <class Cfg, int MIN_CTAS, bool RAGGED>
+__global__ void __launch_bounds__(Cfg::THREADS + 32, MIN_CTAS)
+k_ggemm_f64_ws(const double* __restrict__ Abase, const double* __restrict__ Bbase,
+               double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob, int64_t ntiles,
+               const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start) {
+  static_assert(Cfg::MI == 4 && Cfg::NI == 4, "ragged dispatch below assumes 32x32 warp tiles");
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Bs + Cfg::STAGES * Cfg::B_STAGE);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  constexpr int NCW = Cfg::THREADS / 32;  // consumer warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 32);    // every producer lane arrives when its cp.asyncs have landed
+      mbar_init(&empty_bar[s], NCW);  // one arrival per consumer warp
+    }
+  }
+  __syncthreads();
+
+  int64_t t_beg = blockIdx.x, t_end = ntiles, t_step = gridDim.x;
+  if (slot_start != nullptr) {
+    t_beg = slot_start[blockIdx.x];
+    t_end = slot_start[blockIdx.x + 1];
+    t_step = 1;
+  }
+  int stage = 0;
+  unsigned phase = 0;
+
+  if (warp == NCW) {
+    // ================================ producer warp =====================================
+    // A tile: BM x BK, 16-byte chunks: lane owns k-chunk (lane % 8 [%16 for BK=32]) of rows lane/CPR + i*RPI
+    constexpr int CPR_A = Cfg::BK / 2;            // chunks per A row
+    constexpr int RPI_A = 32 / CPR_A;             // rows covered per pass
+    constexpr int NPASS_A = Cfg::BM / RPI_A;
+    // B tile: BK x BN: lane owns column chunk lane + 32*j of every k row
+    constexpr int CPR_B = Cfg::BN / 2;
+    constexpr int NCH_B = CPR_B / 32;             // chunks per lane per row
+    for (int64_t t = t_beg; t < t_end; t += t_step) {
+      const int4 tile = tiles[t];
+      const t10_gemm_problem p = prob[tile.x];
+      const int m0 = tile.y, n0 = tile.z;
+      const int m_rem = p.m - m0, n_rem = p.n - n0;
+      const bool a16 = ((p.lda & 1) == 0) && ((p.a_off & 1) == 0) && (((uintptr_t)Abase & 15) == 0);
+      const bool b16 = ((p.ldb & 1) == 0) && (((p.b_off + n0) & 1) == 0) && (((uintptr_t)Bbase & 15) == 0);
+      const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
+      const int a_kc = (lane % CPR_A) * 2, a_r0 = lane / CPR_A;
+      const double* a_ptr = Abase + p.a_off + (int64_t)(m0 + a_r0) * p.lda + a_kc;
+      const int64_t a_step = (int64_t)RPI_A * p.lda;
+      const double* b_ptr = Bbase + p.b_off + n0 + lane * 2;
+      for (int kt = 0; kt < KT; ++kt) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int k0 = kt * Cfg::BK;
+        double* as = As + stage * Cfg::A_STAGE + a_r0 * Cfg::LDA + a_kc;
+        const int a_kvalid = max(0, min(2, p.k - k0 - a_kc));  // doubles of this chunk inside K
+#pragma unroll
+        for (int i = 0; i < NPASS_A; ++i) {
+          const int valid = (a_r0 + i * RPI_A < m_rem) ? a_kvalid : 0;
+          const double* g = valid ? a_ptr + i * a_step + k0 : Abase;
+          double* sdst = as + i * RPI_A * Cfg::LDA;
+          if (a16) {
+            cp_async16(sdst, g, valid * 8);
+          } else {
+            cp_async8(sdst, g, valid >= 1 ? 8 : 0);
+            cp_async8(sdst + 1, valid >= 2 ? g + 1 : Abase, valid >= 2 ? 8 : 0);
+          }
+        }
+        double* bsm = Bs + stage * Cfg::B_STAGE + lane * 2;
+        const int k_rows = min(Cfg::BK, p.k - k0);
+#pragma unroll
+        for (int r = 0; r < Cfg::BK; ++r) {
+#pragma unroll
+          for (int j = 0; j < NCH_B; ++j) {
+            const int nc = lane * 2 + j * 64;
+            const int valid = (r < k_rows) ? max(0, min(2, n_rem - nc)) : 0;
+            const double* g = valid ? b_ptr + (int64_t)(k0 + r) * p.ldb + j * 64 : Bbase;
+            double* sdst = bsm + r * Cfg::LDB + j * 64;
+            if (b16) {
+              cp_async16(sdst, g, valid * 8);
+            } else {
+              cp_async8(sdst, g, valid >= 1 ? 8 : 0);
+              cp_async8(sdst + 1, valid >= 2 ? g + 1 : Bbase, valid >= 2 ? 8 : 0);
+            }
+          }
+        }
+        mbar_arrive_cp_async(&full_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    cp_async_wait<0>();
+    asm volatile("cp.async.wait_all;\n" ::);
+    return;
+  }
+
+  // ================================== consumer warps =====================================
+  const int g = lane >> 2, tig = lane & 3;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  for (int64_t t = t_beg; t < t_end; t += t_step) {
+    const int4 tile = tiles[t];
+    const t10_gemm_problem p = prob[tile.x];
+    const int m0 = tile.y, n0 = tile.z;
+    const int m_rem = p.m - m0, n_rem = p.n - n0;
+    const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
+    const int mi_valid = max(0, min(Cfg::MI, (m_rem - wm0 + 7) >> 3));
+    const int ni_valid = max(0, min(Cfg::NI, (n_rem - wn0 + 7) >> 3));
+    const int vcode = (mi_valid == 0 || ni_valid == 0) ? 0 : (RAGGED ? mi_valid * 4 + ni_valid : 20);
+
+    double acc[Cfg::MI][Cfg::NI][2];
+#pragma unroll
+    for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+      mbar_wait(&full_bar[stage], phase);
+      const double* as = As + stage * Cfg::A_STAGE + (wm0 + g) * Cfg::LDA + tig;
+      const double* bs = Bs + stage * Cfg::B_STAGE + tig * Cfg::LDB + wn0 + g;
+      switch (vcode) {
+#define T10_WS_CASE(MV, NV) \
+  case MV * 4 + NV: ws_compute<Cfg, MV, NV>(as, bs, acc); break;
+        T10_WS_CASE(4, 4) T10_WS_CASE(4, 3) T10_WS_CASE(4, 2) T10_WS_CASE(4, 1)
+        T10_WS_CASE(3, 4) T10_WS_CASE(3, 3) T10_WS_CASE(3, 2) T10_WS_CASE(3, 1)
+        T10_WS_CASE(2, 4) T10_WS_CASE(2, 3) T10_WS_CASE(2, 2) T10_WS_CASE(2, 1)
+        T10_WS_CASE(1, 4) T10_WS_CASE(1, 3) T10_WS_CASE(1, 2) T10_WS_CASE(1, 1)
+#undef T10_WS_CASE
+        default: break;  // this warp's 32x32 patch lies outside the sector
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    if (vcode == 0) continue;
     double* C = Cbase + p.c_off;
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
 #pragma unroll
@@ -281,14 +593,50 @@ __global__ void k_probe_dfma(double* out, int iters) {
   if (s == 123.456) out[0] = s;
 }
 
-using CfgA = F64Cfg<64, 64, 32, 32, 4>;     // tile_cfg 0: 128 thr, 75.8 KB smem
-using CfgB = F64Cfg<128, 128, 64, 32, 4>;   // tile_cfg 1: 256 thr, 149.5 KB smem
-using CfgC = F64Cfg<128, 64, 64, 32, 4>;    // tile_cfg 2: 128 thr, 116.7 KB smem
+// even warps: DMMA, odd warps: DFMA (8x the iterations = same FMA count per warp).  Tells whether the
+// tensor DMMA path and the FP64 FMA pipe are separate execution resources on sm_100a.
+__global__ void k_probe_mixed(double* out, int iters) {
+  const int warp = threadIdx.x >> 5;
+  double s = 0;
+  if (warp & 1) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
+    for (int it = 0; it < iters * 8; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+  } else {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  }
+  if (s == 123.456) out[0] = s;
+}
 
-template <class Cfg, int MIN_CTAS>
-static int launch_f64(const double* A, const double* B, double* C, const t10_gemm_problem* prob,
-                      int64_t ntiles, const int32_t* tiles, cudaStream_t st) {
-  auto kern = k_ggemm_f64<Cfg, MIN_CTAS>;
+using CfgA = F64Cfg<64, 64, 32, 32, 4>;       // tile_cfg 0: 128 thr, 75.8 KB smem, 2 CTAs/SM
+using CfgB = F64Cfg<128, 128, 64, 32, 4>;     // tile_cfg 1: 256 thr, 149.5 KB smem
+using CfgC = F64Cfg<128, 64, 64, 32, 4>;      // tile_cfg 2: 128 thr, 116.7 KB smem
+using CfgD = F64Cfg<64, 64, 32, 32, 3>;       // tile_cfg 3: 128 thr, 56.8 KB smem, 3 CTAs/SM
+using CfgE = F64Cfg<64, 64, 32, 32, 3, 32>;   // tile_cfg 4: BK = 32, 107.5 KB smem, 2 CTAs/SM
+using CfgF = F64Cfg<64, 64, 32, 32, 2, 32>;   // tile_cfg 5: BK = 32, 2 stages, 71.7 KB smem, 3 CTAs/SM
+
+// launch == false: only report the number of resident CTA slots (sm_count x CTAs/SM)
+template <class Cfg, int MIN_CTAS, bool RAGGED = true>
+static int launch_f64(bool launch, int* nslots_out, const double* A, const double* B, double* C,
+                      const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
+                      const int32_t* slot_start, int32_t* sched, cudaStream_t st) {
+  auto kern = k_ggemm_f64<Cfg, MIN_CTAS, RAGGED>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
     T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -297,17 +645,81 @@ static int launch_f64(const double* A, const double* B, double* C, const t10_gem
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
     ctas_per_sm = occ;
   }
-  unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles);
+  if (!launch) {
+    *nslots_out = sm_count() * ctas_per_sm;
+    return T10_OK;
+  }
+  unsigned grid;
+  if (slot_start != nullptr) {
+    T10_REQUIRE(nslots >= 1, T10_ERR_INVALID, "slot table without slots");
+    grid = (unsigned)nslots;
+  } else {
+    grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
+  }
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
 
-static bool tile_dims(int cfg, int* bm, int* bn) {
+template <class Cfg, int MIN_CTAS, bool RAGGED = true>
+static int launch_f64_ws(bool launch, int* nslots_out, const double* A, const double* B, double* C,
+                         const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
+                         const int32_t* slot_start, int32_t* /*sched: the ws kernel keeps static schedules*/,
+                         cudaStream_t st) {
+  auto kern = k_ggemm_f64_ws<Cfg, MIN_CTAS, RAGGED>;
+  constexpr int SMEM = Cfg::SMEM_BYTES + 2 * Cfg::STAGES * 8;
+  constexpr int THREADS = Cfg::THREADS + 32;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int occ = 0;
+    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, SMEM));
+    T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
+    ctas_per_sm = occ;
+  }
+  if (!launch) {
+    *nslots_out = sm_count() * ctas_per_sm;
+    return T10_OK;
+  }
+  unsigned grid;
+  if (slot_start != nullptr) {
+    T10_REQUIRE(nslots >= 1, T10_ERR_INVALID, "slot table without slots");
+    grid = (unsigned)nslots;
+  } else {
+    grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
+  }
+  kern<<<grid, THREADS, SMEM, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+static int dispatch_f64(int tile_cfg, bool launch, int* nslots_out, const double* A, const double* B, double* C,
+                        const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
+                        const int32_t* slot_start, int32_t* sched, cudaStream_t st) {
+  switch (tile_cfg) {
+    case 0: return launch_f64<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 1: return launch_f64<CfgB, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 2: return launch_f64<CfgC, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 3: return launch_f64<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 4: return launch_f64<CfgE, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 5: return launch_f64<CfgF, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 10: return launch_f64_ws<CfgA, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 11: return launch_f64_ws<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 12: return launch_f64_ws<CfgE, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 13: return launch_f64_ws<CfgD, 4>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 14: return launch_f64_ws<CfgA, 3, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 6: return launch_f64<CfgA, 2, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 7: return launch_f64<CfgD, 3, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    default: T10_REQUIRE(false, T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
+  }
+}
+
+static bool tile_dims(int cfg, int* bm, int* bn, int* bk) {
   switch (cfg) {
-    case 0: *bm = 64; *bn = 64; return true;
-    case 1: *bm = 128; *bn = 128; return true;
-    case 2: *bm = 128; *bn = 64; return true;
+    case 0: case 3: case 6: case 7: case 10: case 11: case 13: case 14: case 100: *bm = 64; *bn = 64; *bk = 16; return true;
+    case 4: case 5: case 12: *bm = 64; *bn = 64; *bk = 32; return true;
+    case 1: *bm = 128; *bn = 128; *bk = 16; return true;
+    case 2: *bm = 128; *bn = 64; *bk = 16; return true;
     default: return false;
   }
 }
@@ -317,72 +729,103 @@ static bool tile_dims(int cfg, int* bm, int* bn) {
 using namespace t10;
 
 extern "C" int t10_ggemm_tile_shape(int tile_cfg, int* bm, int* bn) {
-  T10_REQUIRE(tile_dims(tile_cfg, bm, bn), T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
+  int bk;
+  T10_REQUIRE(tile_dims(tile_cfg, bm, bn, &bk), T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
+  return T10_OK;
+}
+
+extern "C" int t10_ggemm_slots(int dtype, int tile_cfg, int* nslots) {
+  if (dtype == T10_F64 && tile_cfg != 100)
+    return dispatch_f64(tile_cfg, false, nslots, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
+  *nslots = sm_count() * 4;
   return T10_OK;
 }
 
 extern "C" int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_problem* h_prob,
-                                    int64_t cap, int32_t* h_tiles, int64_t* ntiles) {
-  int bm, bn;
-  T10_REQUIRE(tile_dims(tile_cfg, &bm, &bn), T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
+                                    int64_t nslots, int64_t cap, int32_t* h_tiles,
+                                    int32_t* h_slot_start, int64_t* ntiles) {
+  int bm, bn, bk;
+  T10_REQUIRE(tile_dims(tile_cfg, &bm, &bn, &bk), T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
   struct Tl { int32_t p, m0, n0; int64_t cost; };
   std::vector<Tl> v;
   for (int64_t i = 0; i < nprob; ++i) {
     const t10_gemm_problem& p = h_prob[i];
     T10_REQUIRE(p.m >= 0 && p.n >= 0 && p.k >= 0, T10_ERR_INVALID, "negative GEMM extent");
     if (p.m == 0 || p.n == 0) continue;
+    const int64_t kt = (p.k + bk - 1) / bk;
     for (int m0 = 0; m0 < p.m; m0 += bm)
       for (int n0 = 0; n0 < p.n; n0 += bn) {
         int64_t mm = std::min(bm, p.m - m0), nn = std::min(bn, p.n - n0);
-        // cost model: k-loop length dominates; partial tiles still pay the full MMA tile
-        v.push_back({(int32_t)i, m0, n0, (int64_t)p.k * 1024 + mm * nn / 64});
+        // cost model = DMMA count: k-steps x valid 8x8 fragments (ragged tiles skip empty fragments),
+        // plus a fixed prologue/epilogue term worth about two full k-steps
+        int64_t frags = ((mm + 7) / 8) * ((nn + 7) / 8);
+        v.push_back({(int32_t)i, m0, n0, kt * (bk / 4) * frags + 2 * (bk / 4) * (bm / 8) * (bn / 8)});
       }
   }
   std::stable_sort(v.begin(), v.end(), [](const Tl& a, const Tl& b) { return a.cost > b.cost; });
   *ntiles = (int64_t)v.size();
-  if (h_tiles) {
-    T10_REQUIRE(cap >= (int64_t)v.size(), T10_ERR_INVALID, "tile buffer too small");
-    for (size_t i = 0; i < v.size(); ++i) {
-      h_tiles[4 * i + 0] = v[i].p;
-      h_tiles[4 * i + 1] = v[i].m0;
-      h_tiles[4 * i + 2] = v[i].n0;
-      h_tiles[4 * i + 3] = 0;
-    }
+  if (!h_tiles) return T10_OK;
+  T10_REQUIRE(cap >= (int64_t)v.size(), T10_ERR_INVALID, "tile buffer too small");
+  auto put = [&](size_t dst, const Tl& t) {
+    h_tiles[4 * dst + 0] = t.p;
+    h_tiles[4 * dst + 1] = t.m0;
+    h_tiles[4 * dst + 2] = t.n0;
+    h_tiles[4 * dst + 3] = 0;
+  };
+  if (nslots <= 0 || h_slot_start == nullptr) {
+    for (size_t i = 0; i < v.size(); ++i) put(i, v[i]);
+    return T10_OK;
   }
+  // LPT: heaviest tile to the least-loaded slot; tiles are then stored slot-major
+  std::vector<int64_t> load(nslots, 0);
+  std::vector<std::vector<int>> members(nslots);
+  // min-heap over (load, slot)
+  std::vector<std::pair<int64_t, int>> heap;
+  for (int s2 = 0; s2 < nslots; ++s2) heap.push_back({0, s2});
+  auto cmp = [](const std::pair<int64_t, int>& a, const std::pair<int64_t, int>& b) { return a > b; };
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  for (size_t i = 0; i < v.size(); ++i) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    auto& top = heap.back();
+    members[top.second].push_back((int)i);
+    top.first += v[i].cost;
+    std::push_heap(heap.begin(), heap.end(), cmp);
+  }
+  size_t pos = 0;
+  for (int s2 = 0; s2 < nslots; ++s2) {
+    h_slot_start[s2] = (int32_t)pos;
+    for (int idx : members[s2]) put(pos++, v[idx]);
+  }
+  h_slot_start[nslots] = (int32_t)pos;
   return T10_OK;
 }
 
 extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d_C,
                          int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
-                         const int32_t* d_tiles, t10_stream_t stream) {
+                         const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
+                         int32_t* d_sched, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ntiles == 0 || nprob == 0) return T10_OK;
+  T10_REQUIRE(d_sched == nullptr || d_slot_start == nullptr, T10_ERR_INVALID,
+              "ggemm: dynamic schedule and slot table are mutually exclusive");
   T10_REQUIRE(ntiles > 0 && nprob > 0, T10_ERR_INVALID, "negative counts");
-  if (dtype == T10_F64) {
-    const double* A = (const double*)d_A;
-    const double* B = (const double*)d_B;
-    double* C = (double*)d_C;
-    switch (tile_cfg) {
-      case 0: return launch_f64<CfgA, 2>(A, B, C, d_prob, ntiles, d_tiles, st);
-      case 1: return launch_f64<CfgB, 1>(A, B, C, d_prob, ntiles, d_tiles, st);
-      case 2: return launch_f64<CfgC, 1>(A, B, C, d_prob, ntiles, d_tiles, st);
-      case 100: {  // SIMT cross-check path (64x64 tiles), used by tests only
-        unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 4);
-        k_ggemm_simt<double><<<grid, 256, 0, st>>>(A, B, C, d_prob, ntiles, (const int4*)d_tiles);
-        T10_LAUNCH_CHECK();
-        return T10_OK;
-      }
-      default: T10_REQUIRE(false, T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
-    }
+  if (dtype == T10_F64 && tile_cfg != 100)
+    return dispatch_f64(tile_cfg, true, nullptr, (const double*)d_A, (const double*)d_B, (double*)d_C, d_prob,
+                        ntiles, d_tiles, nslots, d_slot_start, d_sched, st);
+  // SIMT kernels walk the flat tile list (slot tables are ignored: tiles are stored slot-major, any order works)
+  unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 4);
+  if (dtype == T10_F64) {  // cfg 100: cross-check path used by the tests
+    k_ggemm_simt<double><<<grid, 256, 0, st>>>((const double*)d_A, (const double*)d_B, (double*)d_C, d_prob,
+                                               ntiles, (const int4*)d_tiles);
   } else if (dtype == T10_F32) {
     T10_REQUIRE(tile_cfg == 0 || tile_cfg == 100, T10_ERR_INVALID, "fp32 ggemm uses 64x64 tiles (cfg 0)");
-    unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 4);
-    k_ggemm_simt<float><<<grid, 256, 0, st>>>((const float*)d_A, (const float*)d_B, (float*)d_C,
-                                              d_prob, ntiles, (const int4*)d_tiles);
-    T10_LAUNCH_CHECK();
-    return T10_OK;
+    k_ggemm_simt<float><<<grid, 256, 0, st>>>((const float*)d_A, (const float*)d_B, (float*)d_C, d_prob,
+                                              ntiles, (const int4*)d_tiles);
+  } else {
+    T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "ggemm: dtype %d not supported", dtype);
   }
-  T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "ggemm: dtype %d not supported", dtype);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
 }
 
 extern "C" int t10_probe_f64_peak(int use_dmma, int iters, double* tflops, t10_stream_t stream) {
@@ -395,7 +838,8 @@ extern "C" int t10_probe_f64_peak(int use_dmma, int iters, double* tflops, t10_s
   const int blocks = sm_count() * 4, threads = 256;
   for (int rep = 0; rep < 2; ++rep) {  // first rep warms up
     T10_CUDA(cudaEventRecord(e0, st));
-    if (use_dmma) k_probe_dmma<<<blocks, threads, 0, st>>>(d_out, iters);
+    if (use_dmma == 1) k_probe_dmma<<<blocks, threads, 0, st>>>(d_out, iters);
+    else if (use_dmma == 2) k_probe_mixed<<<blocks, threads, 0, st>>>(d_out, iters);
     else k_probe_dfma<<<blocks, threads, 0, st>>>(d_out, iters);
     T10_CUDA(cudaEventRecord(e1, st));
     T10_CUDA(cudaEventSynchronize(e1));
@@ -404,7 +848,7 @@ extern "C" int t10_probe_f64_peak(int use_dmma, int iters, double* tflops, t10_s
   T10_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   // DMMA m8n8k4 = 256 FMA per warp instruction; DFMA = 32 FMA per warp instruction
   double warps = (double)blocks * threads / 32.0;
-  double fma = warps * (double)iters * 16.0 * (use_dmma ? 256.0 : 32.0);
+  double fma = warps * (double)iters * 16.0 * (use_dmma == 1 ? 256.0 : use_dmma == 2 ? 256.0 : 32.0);
   *tflops = 2.0 * fma / (ms * 1e-3) / 1e12;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

@@ -28,57 +28,104 @@ namespace t10 {
 constexpr int RL_THREADS = 256;                 // 8 warps: 4 column groups x 2 row halves
 constexpr int RL_TR = T10_RELAYOUT_TR;          // 32 rows per tile
 constexpr int RL_TC = T10_RELAYOUT_TC;          // 128 columns per tile
-constexpr int RL_UNROLL = 8;
+constexpr int RL_ROWS_PER_THREAD = RL_TR / (RL_THREADS / RL_TC);   // 16
 
-template <typename T, bool CHECK>
+// Dependent-load chain per tile (what bounds a 50 MB relayout after an L2 flush): tile record ->
+// {RR/RC, CR/CC} -> {rowbase, coloff} -> source element.  The tile record carries everything the tile
+// needs (no sector-table indirection) and a thread keeps all its 16 row gathers in flight at once.
+template <typename T, bool CHECK, bool EMIT>
 __global__ void __launch_bounds__(RL_THREADS)
-k_relayout_blocks(const T* __restrict__ src, T* __restrict__ dst, int64_t ntiles,
-                  const int4* __restrict__ tiles, const int64_t* __restrict__ dst_sec,
+k_relayout_blocks(const T* __restrict__ src, T* __restrict__ dst, int32_t* __restrict__ emit, int64_t ntiles,
+                  const t10_relayout_tile* __restrict__ tiles,
                   const int32_t* __restrict__ RR, const int32_t* __restrict__ RC,
                   const int32_t* __restrict__ CR, const int32_t* __restrict__ CC,
                   const int64_t* __restrict__ rowbase, const int32_t* __restrict__ coloff,
                   const int64_t* __restrict__ ket_map, const int64_t* __restrict__ bra_map) {
   __shared__ int32_t s_rr[RL_TR], s_rc[RL_TR];
+  const int tc = threadIdx.x & (RL_TC - 1);
+  const int rbeg = (threadIdx.x / RL_TC) * RL_ROWS_PER_THREAD;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int4 tile = tiles[t];
-    const int64_t* si = dst_sec + (int64_t)tile.x * 8;
-    const int rows = (int)si[0], cols = (int)si[1];
-    const int64_t ks = si[2], bs = si[3], doff = si[4], dld = si[5];
-    const int r0 = tile.y, c0 = tile.z;
-    const int nr = min(RL_TR, rows - r0);
+    const t10_relayout_tile tile = tiles[t];
+    const bool col_ok = tc < tile.nc;
+    int cr = 0, cc = 0;
+    if (col_ok) {
+      cr = CR[tile.cbase + tc];
+      cc = CC[tile.cbase + tc];
+    }
     __syncthreads();  // previous tile done with s_rr/s_rc
     if (threadIdx.x < RL_TR) {
-      int r = threadIdx.x;
-      s_rr[r] = r < nr ? RR[ks + r0 + r] : 0;
-      s_rc[r] = r < nr ? RC[ks + r0 + r] : 0;
+      const int r = threadIdx.x;
+      s_rr[r] = r < tile.nr ? RR[tile.rbase + r] : 0;
+      s_rc[r] = r < tile.nr ? RC[tile.rbase + r] : 0;
     }
     __syncthreads();
-    const int c = c0 + (threadIdx.x & (RL_TC - 1));
-    const int rbeg = (threadIdx.x / RL_TC) * (RL_TR / (RL_THREADS / RL_TC));
-    const int rend = min(nr, rbeg + RL_TR / (RL_THREADS / RL_TC));
-    if (c < cols) {
-      const int cr = CR[bs + c], cc = CC[bs + c];
-      T* out = dst + doff + (int64_t)r0 * dld + c;
-      for (int rb = rbeg; rb < rend; rb += RL_UNROLL) {
-        T v[RL_UNROLL];
+    if (!col_ok) continue;
+    const int rend = min(tile.nr, rbeg + RL_ROWS_PER_THREAD);
+    int64_t addr[RL_ROWS_PER_THREAD];
 #pragma unroll
-        for (int u = 0; u < RL_UNROLL; ++u) {
-          const int r = rb + u;
-          v[u] = T(0);
-          if (r < rend) {
-            const int64_t base = rowbase[s_rr[r] + cr];
-            const int32_t co = coloff[s_rc[r] + cc];
-            bool ok = base >= 0 && co >= 0;
-            if (CHECK && ok)  // Zn layouts (quirk Q3): row and column may sit in different sectors
-              ok = ket_map[2 * (int64_t)(s_rr[r] + cr)] == bra_map[2 * (int64_t)(s_rc[r] + cc)];
-            if (ok) v[u] = src[base + co];
-          }
-        }
+    for (int u = 0; u < RL_ROWS_PER_THREAD; ++u) {
+      const int r = rbeg + u;
+      addr[u] = -1;
+      if (r < rend) {
+        const int srow = s_rr[r] + cr, scol = s_rc[r] + cc;
+        const int64_t base = rowbase[srow];
+        const int32_t co = coloff[scol];
+        bool ok = base >= 0 && co >= 0;
+        if (CHECK && ok)  // Zn layouts (quirk Q3): row and column may sit in different sectors
+          ok = ket_map[2 * (int64_t)srow] == bra_map[2 * (int64_t)scol];
+        if (ok) addr[u] = base + co;
+      }
+    }
+    if (EMIT) {  // plan time: record the source element index of every destination element
+      int32_t* out = emit + tile.dst + tc;
 #pragma unroll
-        for (int u = 0; u < RL_UNROLL; ++u) {
-          const int r = rb + u;
-          if (r < rend) out[(int64_t)r * dld] = v[u];
-        }
+      for (int u = 0; u < RL_ROWS_PER_THREAD; ++u)
+        if (rbeg + u < rend) out[(int64_t)(rbeg + u) * tile.dld] = (int32_t)addr[u];
+      continue;
+    }
+    T v[RL_ROWS_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < RL_ROWS_PER_THREAD; ++u) v[u] = addr[u] >= 0 ? src[addr[u]] : T(0);
+    T* out = dst + tile.dst + tc;
+#pragma unroll
+    for (int u = 0; u < RL_ROWS_PER_THREAD; ++u)
+      if (rbeg + u < rend) out[(int64_t)(rbeg + u) * tile.dld] = v[u];
+  }
+}
+
+// Replay of a relayout through its precomputed element index (built once per plan by the kernel above
+// in EMIT mode): dst[i] = src[index[i]] (index -1: write 0, -2: leave untouched).  Dependent-load chain
+// of length two (index -> element), no tiles, no shared memory: this is what runs on the hot path when
+// the index (4 B per destination element) fits the plan-memory budget.
+constexpr int RI_THREADS = 256;
+constexpr int RI_UNROLL = 4;
+template <typename T>
+__global__ void __launch_bounds__(RI_THREADS)
+k_relayout_index(const T* __restrict__ src, T* __restrict__ dst, const int2* __restrict__ index, int64_t npairs) {
+  struct alignas(2 * sizeof(T)) Pair { T x, y; };
+  const int64_t stride = (int64_t)gridDim.x * RI_THREADS;
+  for (int64_t i0 = (int64_t)blockIdx.x * RI_THREADS + threadIdx.x; i0 < npairs; i0 += stride * RI_UNROLL) {
+    int2 ix[RI_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RI_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      ix[u] = i < npairs ? index[i] : make_int2(-2, -2);
+    }
+    Pair v[RI_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RI_UNROLL; ++u) {
+      v[u].x = ix[u].x >= 0 ? src[ix[u].x] : T(0);
+      v[u].y = ix[u].y >= 0 ? src[ix[u].y] : T(0);
+    }
+#pragma unroll
+    for (int u = 0; u < RI_UNROLL; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= npairs) continue;
+      if (ix[u].x != -2 && ix[u].y != -2) {
+        *reinterpret_cast<Pair*>(dst + 2 * i) = v[u];
+      } else {
+        if (ix[u].x != -2) dst[2 * i] = v[u].x;
+        if (ix[u].y != -2) dst[2 * i + 1] = v[u].y;
       }
     }
   }
@@ -236,28 +283,76 @@ static int launch_permute(const T* src, T* dst, const PermDesc& pd, cudaStream_t
 using namespace t10;
 
 extern "C" int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntiles,
-                                   const int32_t* d_tiles, const int64_t* d_dst_sec,
-                                   const int32_t* d_RR, const int32_t* d_RC, const int32_t* d_CR,
-                                   const int32_t* d_CC, const int64_t* d_rowbase,
-                                   const int32_t* d_coloff, const int64_t* d_src_ket_map,
-                                   const int64_t* d_src_bra_map, t10_stream_t stream) {
+                                   const t10_relayout_tile* d_tiles, const int32_t* d_RR,
+                                   const int32_t* d_RC, const int32_t* d_CR, const int32_t* d_CC,
+                                   const int64_t* d_rowbase, const int32_t* d_coloff,
+                                   const int64_t* d_src_ket_map, const int64_t* d_src_bra_map,
+                                   int32_t* d_emit_index, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ntiles == 0) return T10_OK;
-  const bool chk = d_src_ket_map != nullptr && d_src_bra_map != nullptr;
   T10_REQUIRE(ntiles > 0, T10_ERR_INVALID, "ntiles < 0");
-  unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 8);
-#define T10_RL_LAUNCH(T, CHK)                                                                   \
-  k_relayout_blocks<T, CHK><<<grid, RL_THREADS, 0, st>>>(                                       \
-      (const T*)d_src, (T*)d_dst, ntiles, (const int4*)d_tiles, d_dst_sec, d_RR, d_RC, d_CR, d_CC, \
-      d_rowbase, d_coloff, d_src_ket_map, d_src_bra_map)
+  const bool chk = d_src_ket_map != nullptr && d_src_bra_map != nullptr;
+  if (d_emit_index != nullptr) {  // plan-time pass: element index instead of data
+    unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * 4);
+    if (chk)
+      k_relayout_blocks<double, true, true><<<grid, RL_THREADS, 0, st>>>(
+          nullptr, nullptr, d_emit_index, ntiles, d_tiles, d_RR, d_RC, d_CR, d_CC, d_rowbase, d_coloff,
+          d_src_ket_map, d_src_bra_map);
+    else
+      k_relayout_blocks<double, false, true><<<grid, RL_THREADS, 0, st>>>(
+          nullptr, nullptr, d_emit_index, ntiles, d_tiles, d_RR, d_RC, d_CR, d_CC, d_rowbase, d_coloff,
+          d_src_ket_map, d_src_bra_map);
+    T10_LAUNCH_CHECK();
+    return T10_OK;
+  }
+  static int occ[4] = {0, 0, 0, 0};
+#define T10_RL_LAUNCH(T, CHK, SLOT)                                                                   \
+  do {                                                                                                \
+    auto kern = k_relayout_blocks<T, CHK, false>;                                                     \
+    if (occ[SLOT] == 0) {                                                                             \
+      T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[SLOT], kern, RL_THREADS, 0));       \
+      if (occ[SLOT] < 1) occ[SLOT] = 1;                                                               \
+    }                                                                                                 \
+    unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * occ[SLOT]);             \
+    kern<<<grid, RL_THREADS, 0, st>>>((const T*)d_src, (T*)d_dst, nullptr, ntiles, d_tiles, d_RR,     \
+                                      d_RC, d_CR, d_CC, d_rowbase, d_coloff, d_src_ket_map,           \
+                                      d_src_bra_map);                                                 \
+  } while (0)
   if (dtype == T10_F64) {
-    if (chk) T10_RL_LAUNCH(double, true); else T10_RL_LAUNCH(double, false);
+    if (chk) T10_RL_LAUNCH(double, true, 0); else T10_RL_LAUNCH(double, false, 1);
   } else if (dtype == T10_F32) {
-    if (chk) T10_RL_LAUNCH(float, true); else T10_RL_LAUNCH(float, false);
+    if (chk) T10_RL_LAUNCH(float, true, 2); else T10_RL_LAUNCH(float, false, 3);
   } else {
     T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "relayout: dtype %d not supported", dtype);
   }
 #undef T10_RL_LAUNCH
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+extern "C" int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n,
+                                  const int32_t* d_index, t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return T10_OK;
+  T10_REQUIRE(n > 0 && (n & 1) == 0, T10_ERR_INVALID, "index length must be even");
+  T10_REQUIRE(((uintptr_t)d_dst & 15) == 0 && ((uintptr_t)d_index & 7) == 0, T10_ERR_INVALID,
+              "relayout_index: destination must be 16-byte aligned");
+  const int64_t npairs = n / 2;
+  static int occ = 0;
+  if (occ == 0) {
+    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relayout_index<double>, RI_THREADS, 0));
+    if (occ < 1) occ = 1;
+  }
+  unsigned grid = (unsigned)std::min<int64_t>(ceil_div(npairs, (int64_t)RI_THREADS * RI_UNROLL),
+                                              (int64_t)sm_count() * occ);
+  if (dtype == T10_F64)
+    k_relayout_index<double><<<grid, RI_THREADS, 0, st>>>((const double*)d_src, (double*)d_dst,
+                                                          (const int2*)d_index, npairs);
+  else if (dtype == T10_F32)
+    k_relayout_index<float><<<grid, RI_THREADS, 0, st>>>((const float*)d_src, (float*)d_dst,
+                                                         (const int2*)d_index, npairs);
+  else
+    T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "relayout_index: dtype %d not supported", dtype);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
