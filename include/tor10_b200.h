@@ -147,9 +147,11 @@ int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n, con
 int t10_permute_dense(int dtype, const void* d_src, void* d_dst, int rank,
                       const int64_t* h_shape, const int64_t* h_src_strides, t10_stream_t stream);
 
-/* out[r, c] = a[r, c] * diag[c] (side = 1, column scaling) or diag[r] * a[r, c] (side = 0). */
-int t10_diag_scale(int dtype, const void* d_a, const void* d_diag, void* d_out, int64_t rows,
-                   int64_t cols, int side, t10_stream_t stream);
+/* Scaling by a diagonal operand without densifying it: a viewed as [outer, d, inner] (contiguous,
+ * row-major), out[o, i, j] = a[o, i, j] * diag[i].  (inner = 1: column scaling of an [outer, d]
+ * matrix; outer = 1: row scaling of a [d, inner] matrix.)                                   */
+int t10_diag_scale(int dtype, const void* d_a, const void* d_diag, void* d_out, int64_t outer,
+                   int64_t d, int64_t inner, t10_stream_t stream);
 
 /* ------------------------------------------------------------------ family 3 ---- */
 

@@ -443,12 +443,70 @@ def gen_bond_kats():
     print("bond: 12")
 
 
+def gen_itebd():
+    """Config 1 (iTEBD.py:75-136) driven through the unmodified reference library from a seeded numpy
+    initial state: the per-step energies are the golden trajectory for oracle/itebd_numpy.py and for the
+    product's examples/itebd.py."""
+    import copy
+    chi, J, Hx, nsteps = 8, 1.0, 0.5, 40
+    rng = np.random.Generator(np.random.PCG64(1234))
+    init = {"A": rng.random((chi, 2, chi)), "B": rng.random((chi, 2, chi)), "la": rng.random(chi), "lb": rng.random(chi)}
+    Tt = tor10
+    dev = torch.device("cpu")
+
+    def op(e):
+        t = Tt.UniTensor(bonds=[Tt.Bond(2), Tt.Bond(2)], rowrank=1, dtype=torch.float64, device=dev)
+        t.SetElem(e)
+        return t
+    Sz, Sx, I = op([1, 0, 0, -1]) * J, op([0, 1, 1, 0]) * Hx, op([1, 0, 0, 1])
+    H = Tt.Otimes(Sx, I) + Tt.Otimes(I, Sx) + Tt.Otimes(Sz, Sz)
+    H = H.Reshape([4, 4], new_labels=[0, 1], rowrank=1)
+    eH = Tt.ExpH(H * -0.1).Reshape([2, 2, 2, 2], new_labels=[0, 1, 2, 3], rowrank=2)
+    H = H.Reshape([2, 2, 2, 2], new_labels=[0, 1, 2, 3], rowrank=2)
+    A = Tt.UniTensor(bonds=[Tt.Bond(chi), Tt.Bond(2), Tt.Bond(chi)], rowrank=1, labels=[-1, 0, -2])
+    B = Tt.UniTensor(bonds=A.bonds, rowrank=1, labels=[-3, 1, -4])
+    la = Tt.UniTensor(bonds=[Tt.Bond(chi), Tt.Bond(chi)], rowrank=1, labels=[-2, -3], is_diag=True)
+    lb = Tt.UniTensor(bonds=[Tt.Bond(chi), Tt.Bond(chi)], rowrank=1, labels=[-4, -5], is_diag=True)
+    for t, k in ((A, "A"), (B, "B"), (la, "la"), (lb, "lb")):
+        t.Storage = torch.from_numpy(init[k].copy())
+    energies = []
+    for i in range(nsteps):
+        A.SetLabels([-1, 0, -2]); B.SetLabels([-3, 1, -4]); la.SetLabels([-2, -3]); lb.SetLabels([-4, -5])
+        X = Tt.Contract(Tt.Contract(A, la), Tt.Contract(B, lb))
+        lb.SetLabel(-1, idx=1)
+        X = Tt.Contract(lb, X)
+        Xt = copy.deepcopy(X)
+        XNorm = Tt.Contract(X, Xt)
+        XH = Tt.Contract(X, H)
+        XH.SetLabels([-4, -5, 0, 1])
+        XHX = Tt.Contract(Xt, XH)
+        XeH = Tt.Contract(X, eH)
+        energies.append((XHX.Storage / XNorm.Storage).item())
+        XeH.Permute([-4, 2, 3, -5], by_label=True)
+        XeH.Reshape_([chi * 2, chi * 2], rowrank=1)
+        A, la, B = Tt.Svd_truncate(XeH, chi)
+        la *= la.Norm() ** -1
+        A = A.Reshape([chi, 2, chi], new_labels=[-1, 0, -2], rowrank=1)
+        B = B.Reshape([chi, 2, chi], new_labels=[-3, 1, -4], rowrank=1)
+        lb_inv = Tt.Inverse(lb)
+        A = Tt.Contract(lb_inv, A)
+        B = Tt.Contract(B, lb_inv)
+        A, B = B, A
+        la, lb = lb, la
+    out = dict(init)
+    out["energies"] = np.array(energies)
+    out["specs"] = np.array(json.dumps({"chi": chi, "J": J, "Hx": Hx, "nsteps": nsteps}))
+    np.savez_compressed(os.path.join(HERE, "itebd.npz"), **out)
+    print("itebd: %d steps, E[-1] = %.9f" % (nsteps, energies[-1]))
+
+
 if __name__ == "__main__":
     gen_bond_kats()
     gen_blockmap()
     gen_relayout()
     gen_contract_sym()
     gen_dense()
+    gen_itebd()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -410,3 +410,22 @@ def test_network_symmetric_extension(T):
     oc = orc.contract_sym(osym(A, seed=31), osym(B, seed=32))
     for x, y in zip(blocks_np(Rc), oc.blocks):
         assert rel_err(x, y) <= TOL64
+
+
+# ---- config 1: iTEBD end to end ---------------------------------------------------------------
+def test_itebd_trajectory_matches_reference(T):
+    """examples/itebd.py (10 Contract + Svd_truncate + Inverse per step on the GPU kernels) from the seeded
+    initial state of tests/golden/itebd.npz: energies == the unmodified reference's, step by step."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("itebd_example", os.path.join(root, "examples", "itebd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    z = np.load(os.path.join(root, "tests", "golden", "itebd.npz"))
+    sp = json.loads(str(z["specs"]))
+    init = {k: z[k] for k in ("A", "B", "la", "lb")}
+    out = ex.run(sp["J"], sp["Hx"], sp["chi"], 0.0, max_steps=sp["nsteps"], init=init)
+    got = np.array(out["energies"])
+    assert got.shape == z["energies"].shape
+    assert np.abs(got - z["energies"]).max() <= 1e-9

@@ -3,6 +3,8 @@
   * fixtures produced by the unmodified reference (tests/golden/make_golden.py).
 Integer maps exact; fp64 exact here too (pure data movement / same numpy matmul order is
 not guaranteed, so values use 1e-13)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -261,3 +263,21 @@ def test_network_goldens(golden):
 def test_gauss_u1_generator():
     qs, deg = orc.gauss_u1_degeneracies(4096, -20, 19, 6.0)
     assert len(qs) == 40 and deg.sum() == 4096 and deg.min() == 1 and deg.max() == 271
+
+
+def test_itebd_oracle_trajectory(golden):
+    """oracle/itebd_numpy.py follows the reference's iTEBD.py loop: 40 energies from the same initial state."""
+    import json
+    from oracle import itebd_numpy as it
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "itebd.npz"))
+    sp = json.loads(str(z["specs"]))
+    init = {k: z[k] for k in ("A", "B", "la", "lb")}
+    r = it.run(sp["J"], sp["Hx"], sp["chi"], 0.0, max_steps=sp["nsteps"], init=init)
+    assert np.abs(np.array(r["energies"]) - z["energies"]).max() <= 1e-12
+
+
+def test_itebd_oracle_energy():
+    """Converged energy of config 1 (reference run in the build container: E = -1.252868)."""
+    from oracle import itebd_numpy as it
+    r = it.run(1.0, 0.5, 16, 1e-9, max_steps=20000, seed=3)
+    assert abs(r["E"] - (-1.2528)) < 5e-4

@@ -1,0 +1,184 @@
+#!/usr/bin/env python
+"""Secondary measurements of SURVEY 8(d) (not the driver's bench line): prints one JSON object per item.
+
+  C1   iTEBD chi=32 (examples/itebd.py): steps/s on the GPU path, Svd_truncate share timed separately,
+       numpy port of the reference loop on the host cores beside it
+  C2   dense rank-4 Contract chi=1024, d=2 (permute + GEMM): GFLOP/s, permute GB/s alone
+  C3a  stage split + the reference torch path ON THE GPU (per-sector torch.matmul loop on pre-permuted
+       blocks = the cuBLAS bar), C3b MPS-MPO-MPS environment step
+  F1   block-map build latency (family 1) at C3a sizes, plan build (cold) vs replay (warm)
+"""
+import importlib.util
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tor10_b200 as T  # noqa: E402
+from helpers import psym  # noqa: E402
+from oracle import tor10_oracle as orc  # noqa: E402  (synthetic-leg generator + host baselines only)
+
+dev = torch.device("cuda", 0)
+flush = torch.empty(256 * 1024 * 1024 // 8, device=dev, dtype=torch.float64)
+
+
+def timed(fn, n=30, warm=3):
+    for _ in range(warm):
+        fn()
+    evs = []
+    for _ in range(n):
+        flush.fill_(1.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return float(np.median([s.elapsed_time(e) for s, e in evs]))
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def c1_itebd(chi=32, steps=300):
+    spec = importlib.util.spec_from_file_location("itebd_example", os.path.join(ROOT, "examples", "itebd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    from oracle import itebd_numpy as it
+    rng = np.random.Generator(np.random.PCG64(7))
+    init = {"A": rng.random((chi, 2, chi)), "B": rng.random((chi, 2, chi)), "la": rng.random(chi), "lb": rng.random(chi)}
+    ex.run(1.0, 0.5, chi, 0.0, max_steps=20, init=init, check_every=10 ** 9)      # warm-up: plans, cuSOLVER handles
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = ex.run(1.0, 0.5, chi, 0.0, max_steps=steps, init=init, check_every=steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # Svd_truncate alone (torch/cuSOLVER on device), same matrix size
+    M = T.UniTensor(bonds=[T.Bond(2 * chi), T.Bond(2 * chi)], rowrank=1, device=dev).Rand()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(50):
+        T.Svd_truncate(M, chi)
+    torch.cuda.synchronize()
+    svd_ms = (time.perf_counter() - t1) / 50 * 1e3
+    t2 = time.perf_counter()
+    ref = it.run(1.0, 0.5, chi, 0.0, max_steps=steps, init=init)
+    dtc = time.perf_counter() - t2
+    emit(item="C1 iTEBD TFIM chi=%d" % chi, steps=steps, steps_per_s=steps / dt, ms_per_step=dt / steps * 1e3,
+         svd_truncate_ms=svd_ms, E=out["E"], E_cpu_port=ref["E"], abs_dE=abs(out["E"] - ref["E"]),
+         cpu_port_steps_per_s=steps / dtc, cpu_cores=os.cpu_count(),
+         note="wall clock incl. Python host code; one .item() sync at the end; reference CPU (8 vCPU, build "
+              "container): 218 steps/s")
+
+
+def c2_dense(chi=1024, d=2):
+    g = torch.Generator(device="cpu").manual_seed(2)
+    t1 = T.UniTensor(bonds=[T.Bond(chi), T.Bond(d), T.Bond(d), T.Bond(chi)], rowrank=2, labels=[0, 2, 1, 3], device=dev)
+    t2 = T.UniTensor(bonds=[T.Bond(d), T.Bond(chi), T.Bond(d), T.Bond(chi)], rowrank=2, labels=[2, 3, 4, 5], device=dev)
+    t1.Storage = torch.rand(t1.Storage.shape, generator=g, dtype=torch.float64).to(dev)
+    t2.Storage = torch.rand(t2.Storage.shape, generator=g, dtype=torch.float64).to(dev)
+    flops = 2.0 * (chi * d) ** 3
+    ms = timed(lambda: T.Contract(t1, t2), n=20)
+    want = torch.tensordot(t1.Storage, t2.Storage, dims=([1, 3], [0, 1]))
+    got = T.Contract(t1, t2).Storage
+    err = float((got - want).abs().max() / want.abs().max())
+    ms_torch = timed(lambda: torch.tensordot(t1.Storage, t2.Storage, dims=([1, 3], [0, 1])), n=20)
+    x = t1.Storage.permute(0, 2, 1, 3)
+    ms_perm = timed(lambda: T.UniTensor._contiguous_dense(x), n=30)
+    y = t1.Storage.reshape(chi * d, d * chi).t()
+    ms_tr = timed(lambda: T.UniTensor._contiguous_dense(y), n=30)
+    nbytes = 2.0 * 8 * t1.Storage.numel()
+    emit(item="C2 dense rank-4 Contract chi=%d d=%d" % (chi, d), gflops=flops / ms / 1e6, ms=ms, rel_err_vs_torch=err,
+         torch_tensordot_gpu_gflops=flops / ms_torch / 1e6, permute_rows_GBs=nbytes / ms_perm / 1e6,
+         permute_rows_ms=ms_perm, transpose_2048_GBs=nbytes / ms_tr / 1e6, transpose_ms=ms_tr)
+
+
+def c3(chi=4096):
+    from bench import c3a_specs
+    A, B = c3a_specs(chi)
+    a, b = psym(T, A, seed=1003, device=dev), psym(T, B, seed=1004, device=dev)
+    plan = T._plan.get_contract_plan(a, b)
+    ms = timed(lambda: T.Contract(a, b), n=50)
+    # the reference's torch path on the GPU: per-sector torch.matmul on pre-permuted blocks
+    ap = a.Permute([0, 2, 1, 3], rowrank=2).Contiguous() if False else None
+    a2 = psym(T, A, seed=1003, device=dev)
+    a2.Permute([0, 2, 1, 3], rowrank=2)
+    a2c = a2.Contiguous()
+    Ab, Bb = list(a2c.Storage), list(b.Storage)
+    pairs = [(ab, bb) for _, ab, bb in plan.matched]
+
+    def ref_loop():
+        return [torch.matmul(Ab[i], Bb[j]) for i, j in pairs]
+    ms_ref = timed(ref_loop, n=30)
+    emit(item="C3a U1 Contract chi=%d" % chi, ms=ms, gflops=plan.flops_total / ms / 1e6,
+         reference_torch_path_on_gpu_ms=ms_ref, reference_torch_path_on_gpu_gflops=plan.flops_total / ms_ref / 1e6,
+         note="reference path = its per-sector torch.matmul loop (UniTensor.py:3727-3741) on already-relayouted "
+              "blocks, i.e. cuBLAS DGEMM x%d launches, relayout NOT included" % len(pairs))
+    # C3b: L[(x, w); (a)] x A[(a); (s, b)]
+    v = orc.gauss_u1_qnums(chi, -20, 19, 6.0).tolist()
+    u1 = [["U1", 0]]
+    w = [[0], [0], [0], [2], [-2]]
+    p = [[1], [-1]]
+    Ls = {"bonds": [{"dim": chi, "btype": -1, "qnums": v, "syms": u1}, {"dim": 5, "btype": -1, "qnums": w, "syms": u1},
+                    {"dim": chi, "btype": 1, "qnums": v, "syms": u1}], "rowrank": 2, "labels": [10, 11, 12]}
+    As = {"bonds": [{"dim": chi, "btype": -1, "qnums": v, "syms": u1}, {"dim": 2, "btype": 1, "qnums": p, "syms": u1},
+                    {"dim": chi, "btype": 1, "qnums": v, "syms": u1}], "rowrank": 1, "labels": [12, 13, 14]}
+    for sp in (Ls, As):
+        for bd in sp["bonds"]:
+            bd["qnums"] = sorted(bd["qnums"], reverse=True)
+    L, Am = psym(T, Ls, seed=1005, device=dev), psym(T, As, seed=1006, device=dev)
+    pl = T._plan.get_contract_plan(L, Am)
+    msb = timed(lambda: T.Contract(L, Am), n=50)
+    emit(item="C3b MPS-MPO-MPS environment step chi=%d" % chi, sectors=len(pl.matched), gflop=pl.flops_total / 1e9,
+         ms=msb, gflops=pl.flops_total / msb / 1e6)
+
+
+def f1_blockmap(chi=4096):
+    from bench import c3a_specs
+    A, B = c3a_specs(chi)
+    T._plan.clear_caches()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a = psym(T, A, device=dev)
+    torch.cuda.synchronize()
+    t_ctor = time.perf_counter() - t0
+    b = psym(T, B, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    T.Contract(a, b)
+    torch.cuda.synchronize()
+    t_cold = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(20):
+        T.Contract(a, b)
+    torch.cuda.synchronize()
+    t_warm = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        psym(T, A, device=dev)
+    torch.cuda.synchronize()
+    t_ctor_warm = (time.perf_counter() - t0) / 20
+    emit(item="F1 block map / plans chi=%d" % chi, first_UniTensor_ctor_ms=t_ctor * 1e3, cached_ctor_ms=t_ctor_warm * 1e3,
+         first_Contract_ms_plan_build=t_cold * 1e3, replay_Contract_wall_ms=t_warm * 1e3,
+         note="reference (8 vCPU): block-map build 22.8 ms per tensor, executed 3x per Contract; full Contract "
+              "68.3 ms without relayout (SURVEY 6)")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["f1", "c3", "c2", "c1"]
+    if "f1" in which:
+        f1_blockmap()
+    if "c3" in which:
+        c3()
+    if "c2" in which:
+        c2_dense()
+    if "c1" in which:
+        c1_itebd()
+        c1_itebd(chi=256, steps=40)

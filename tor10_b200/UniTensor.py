@@ -739,10 +739,10 @@ class UniTensor:
             return x
         _lib.require_cuda_tensor(x, "dense relayout")
         out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(_lib.load().t10_permute_dense(
-                _lib.dtype_code(x.dtype), x.data_ptr(), out.data_ptr(), x.dim(), _lib.np_ptr(_lib.i64(list(x.shape))),
-                _lib.np_ptr(_lib.i64(list(x.stride()))), _lib.stream_ptr()))
+                _lib.dtype_code(x.dtype), x.data_ptr(), out.data_ptr(), x.dim(), _lib.i64_args(x.shape),
+                _lib.i64_args(x.stride()), _lib.stream_ptr()))
         return out
 
     def is_contiguous(self):
@@ -1046,8 +1046,11 @@ def Load(filename):
     return tmp
 
 
+_GEMM_GROUPS = {}
+
+
 def _dense_gemm(A2, B2):
-    """[M,K] x [K,N] on the family-3 kernel (single-problem group)."""
+    """[M,K] x [K,N] on the family-3 kernel (single-problem group, cached per shape)."""
     M, K = A2.shape
     N = B2.shape[1]
     _lib.require_cuda_tensor(A2, "contraction")
@@ -1058,31 +1061,90 @@ def _dense_gemm(A2, B2):
         return out
     if K == 0:
         return out.zero_()
-    key = ("dense", M, N, K, A2.dtype, _plan._dev_index(A2.device))
-    grp = _plan._CONTRACTS.get(key)
+    key = (M, N, K, A2.dtype, A2.device.index)
+    grp = _GEMM_GROUPS.get(key)
     if grp is None:
         prob = np.zeros(1, dtype=_lib.GEMM_PROBLEM_DTYPE)
         prob[0] = (0, 0, 0, M, N, K, K, N, N)
         grp = _plan.GemmGroup(prob, A2.device, A2.dtype)
-        _plan._CONTRACTS[key] = grp
-    with torch.cuda.device(A2.device):
-        grp.run(A2, B2, out)
+        _GEMM_GROUPS[key] = grp
+    grp.run(A2, B2, out)
+    return out
+
+
+def _diag_scale(x, diag, axis):
+    """x scaled along `axis` by the 1-D tensor `diag` (family-2 kernel t10_diag_scale); x is made contiguous."""
+    x = UniTensor._contiguous_dense(x)
+    _lib.require_cuda_tensor(x, "contraction with a diagonal tensor")
+    out = torch.empty_like(x)
+    shp = x.shape
+    outer = 1
+    for s_ in shp[:axis]:
+        outer *= int(s_)
+    inner = 1
+    for s_ in shp[axis + 1:]:
+        inner *= int(s_)
+    _lib.check(_lib.load().t10_diag_scale(_lib.dtype_code(x.dtype), x.data_ptr(), diag.contiguous().data_ptr(),
+                                          out.data_ptr(), outer, int(shp[axis]), inner, _lib.stream_ptr()))
     return out
 
 
 def _tensordot(ta, tb, a_ind, b_ind):
     """torch.tensordot(ta, tb, dims=(a_ind, b_ind)) on the family-2 permute + family-3 GEMM kernels."""
-    a_free = [i for i in range(ta.dim()) if i not in set(a_ind)]
-    b_free = [i for i in range(tb.dim()) if i not in set(b_ind)]
+    sa, sb = set(a_ind), set(b_ind)
+    a_free = [i for i in range(ta.dim()) if i not in sa]
+    b_free = [i for i in range(tb.dim()) if i not in sb]
     A = UniTensor._contiguous_dense(ta.permute(a_free + list(a_ind)))
     B = UniTensor._contiguous_dense(tb.permute(list(b_ind) + b_free))
     K = 1
     for i in a_ind:
-        K *= ta.shape[i]
-    M = A.numel() // max(K, 1) if K else int(np.prod([ta.shape[i] for i in a_free], dtype=np.int64))
-    N = B.numel() // max(K, 1) if K else int(np.prod([tb.shape[i] for i in b_free], dtype=np.int64))
+        K *= int(ta.shape[i])
+    M = 1
+    for i in a_free:
+        M *= int(ta.shape[i])
+    N = 1
+    for i in b_free:
+        N *= int(tb.shape[i])
     out = _dense_gemm(A.reshape(M, K), B.reshape(K, N))
     return out.reshape([ta.shape[i] for i in a_free] + [tb.shape[i] for i in b_free])
+
+
+def _label_match_small(la, lb):
+    """Same result as `_plan.label_match` (np.intersect1d / setdiff1d, UniTensor.py:3686-3689) without the
+    numpy set machinery: common labels ascending, their positions, free positions ascending."""
+    la, lb = la.tolist(), lb.tolist()
+    pb = {l: i for i, l in enumerate(lb)}
+    same = sorted(l for l in la if l in pb)
+    pa = {l: i for i, l in enumerate(la)}
+    a_ind = [pa[l] for l in same]
+    b_ind = [pb[l] for l in same]
+    sa, sb = set(a_ind), set(b_ind)
+    return same, a_ind, b_ind, [i for i in range(len(la)) if i not in sa], [i for i in range(len(lb)) if i not in sb]
+
+
+def _dense_result(a, b, tmp, a_free, b_free):
+    """Wrap a dense contraction result: a's free bonds then b's, rows-first reorder applied lazily
+    (UniTensor.py:3773-3790)."""
+    new_io = [x >= a.rowrank for x in a_free] + [x >= b.rowrank for x in b_free]
+    # np.argsort of booleans in the reference is stable for the ranks that occur; stated explicitly here
+    mapper = [i for i, v in enumerate(new_io) if not v] + [i for i, v in enumerate(new_io) if v]
+    src = [(a, i) for i in a_free] + [(b, i) for i in b_free]
+    out = UniTensor.__new__(UniTensor)
+    out.name = ""
+    out.bonds = np.array([copy.copy(src[m][0].bonds[src[m][1]]) for m in mapper], dtype=object)
+    out.labels = np.array([src[m][0].labels[src[m][1]] for m in mapper], dtype=np.int64)
+    out._dense, out._arena, out._blocks, out._layout = None, None, None, None
+    out._mapper, out._inv_mapper, out._contiguous, out._bq = None, None, True, None
+    out.is_braket, out.braket = None, None
+    out.rowrank = len(new_io) - sum(new_io)
+    out.is_symm, out.is_diag = False, False
+    if a.braket is not None:
+        out.braket = np.array([src[m][0].braket[src[m][1]] for m in mapper], dtype=np.int64)
+        out._check_braket()
+    if len(mapper) and mapper != list(range(len(mapper))):
+        tmp = tmp.permute(*mapper)
+    out._dense = tmp
+    return out
 
 
 def Contract(a, b):
@@ -1095,42 +1157,38 @@ def Contract(a, b):
     if a.is_symm:
         return _plan.get_contract_plan(a, b).run(a, b)
 
-    same, a_ind, b_ind, a_free, b_free = _plan.label_match(a.labels, b.labels)
-    # diagonal operands are densified (UniTensor.py:3756-3765)
-    tmpa = torch.diag(a._dense) if a.is_diag else a._dense
-    tmpb = torch.diag(b._dense) if b.is_diag else b._dense
+    same, a_ind, b_ind, a_free, b_free = _label_match_small(a.labels, b.labels)
     if len(same):
         if a.braket is not None:
-            if False in np.unique((a.braket[a_ind] + b.braket[b_ind]) == 0):
+            if any(a.braket[i] + b.braket[j] != 0 for i, j in zip(a_ind, b_ind)):
                 raise Exception("Contract(a,b)", "[ERROR] bra-bond can only contract with ket-bond")
-        tmp = _tensordot(tmpa, tmpb, a_ind.tolist(), b_ind.tolist())
-        new_bonds = np.concatenate([copy.deepcopy(a.bonds[a_free]), copy.deepcopy(b.bonds[b_free])])
-        new_io = [(int(x) >= a.rowrank) for x in a_free] + [(int(x) >= b.rowrank) for x in b_free]
-        new_labels = np.concatenate([a.labels[a_free], b.labels[b_free]])
-        new_braket = None if a.braket is None else np.concatenate([a.braket[a_free], b.braket[b_free]])
-    else:
-        # outer product (UniTensor.py:3825-3880): rank-1 GEMM [M,1]x[1,N]
-        _lib.require_cuda_tensor(tmpa, "contraction")
+        with _lib.on_device(a._dense.device):
+            # a diagonal operand sharing ONE bond scales the other tensor along that bond; the reference
+            # densifies it with torch.diag and runs a chi^3 GEMM (UniTensor.py:3756-3765)
+            if b.is_diag and not a.is_diag and len(same) == 1:
+                ax = a_ind[0]
+                t = _diag_scale(a._dense, b._dense, ax)
+                order = [i for i in range(t.dim()) if i != ax] + [ax]
+                tmp = t.permute(*order) if order != list(range(t.dim())) else t
+            elif a.is_diag and not b.is_diag and len(same) == 1:
+                ax = b_ind[0]
+                t = _diag_scale(b._dense, a._dense, ax)
+                order = [ax] + [i for i in range(t.dim()) if i != ax]
+                tmp = t.permute(*order) if order != list(range(t.dim())) else t
+            else:
+                tmpa = torch.diag(a._dense) if a.is_diag else a._dense
+                tmpb = torch.diag(b._dense) if b.is_diag else b._dense
+                tmp = _tensordot(tmpa, tmpb, a_ind, b_ind)
+        return _dense_result(a, b, tmp, a_free, b_free)
+    # outer product (UniTensor.py:3825-3880): rank-1 GEMM [M,1]x[1,N]
+    tmpa = torch.diag(a._dense) if a.is_diag else a._dense
+    tmpb = torch.diag(b._dense) if b.is_diag else b._dense
+    _lib.require_cuda_tensor(tmpa, "contraction")
+    with _lib.on_device(tmpa.device):
         A2 = UniTensor._contiguous_dense(tmpa).reshape(-1, 1)
         B2 = UniTensor._contiguous_dense(tmpb).reshape(1, -1)
         tmp = _dense_gemm(A2, B2).reshape(list(tmpa.shape) + list(tmpb.shape))
-        new_bonds = np.concatenate([copy.deepcopy(a.bonds), copy.deepcopy(b.bonds)])
-        new_io = [(x >= a.rowrank) for x in range(len(a.bonds))] + [(x >= b.rowrank) for x in range(len(b.bonds))]
-        new_labels = np.concatenate([a.labels, b.labels])
-        new_braket = None if a.braket is None else np.concatenate([a.braket, b.braket])
-    new_io = np.array(new_io, dtype=bool)
-    if len(new_labels):
-        # rows-first reorder, lazily (UniTensor.py:3773-3784).  np.argsort of booleans in the reference is
-        # stable for the ranks that occur; stated explicitly here.
-        mapper = np.argsort(new_io, kind="stable")
-        new_bonds = new_bonds[mapper]
-        new_labels = new_labels[mapper]
-        if new_braket is not None:
-            new_braket = new_braket[mapper]
-        tmp = tmp.permute(*[int(m) for m in mapper])
-    out = UniTensor(bonds=new_bonds, labels=new_labels, rowrank=int((~new_io).sum()), check=False)
-    out._mac(braket=new_braket, torch_tensor=tmp)
-    return out
+    return _dense_result(a, b, tmp, list(range(len(a.labels))), list(range(len(b.labels))))
 
 
 def _CombineBonds(a, idxs, new_label, permute_back):

@@ -63,7 +63,7 @@ SIGNATURES = {
     "t10_relayout_blocks": [_i, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "t10_relayout_index": [_i, _p, _p, _l, _p, _p],
     "t10_permute_dense": [_i, _p, _p, _i, _p, _p, _p],
-    "t10_diag_scale": [_i, _p, _p, _p, _l, _l, _i, _p],
+    "t10_diag_scale": [_i, _p, _p, _p, _l, _l, _l, _p],
     "t10_ggemm_tile_shape": [_i, _p, _p],
     "t10_ggemm_slots": [_i, _i, _p],
     "t10_ggemm_plan_tiles": [_i, _l, _p, _l, _l, _p, _p, _p],
@@ -115,7 +115,34 @@ def require_cuda_tensor(x, what):
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (raw handle, no Stream object)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+class on_device:
+    """`with torch.cuda.device(d)` that does nothing (and costs nothing) when d is already current."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.type == "cuda" else None
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch._C._cuda_getDevice()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def i64_args(vals):
+    """small int64 host array for an ABI call (cheaper than building a numpy array)"""
+    return (C.c_int64 * len(vals))(*vals)
 
 
 def dtype_code(dt):

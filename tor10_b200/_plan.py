@@ -442,7 +442,7 @@ class ContractPlan:
         dt = a.dtype
         if b.dtype != dt:
             raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (dt, b.dtype))
-        with torch.cuda.device(a.device):
+        with _lib.on_device(a.device):
             A = a._arena_tensor()
             B = b._arena_tensor()
             if self.rel_a is not None:

@@ -226,15 +226,14 @@ k_permute_gather(const T* __restrict__ src, T* __restrict__ dst, const __grid_co
   }
 }
 
+// a viewed as [outer, d, inner] (row-major): out[o, i, j] = a[o, i, j] * diag[i]
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_diag_scale(const T* __restrict__ a, const T* __restrict__ diag, T* __restrict__ out,
-             int64_t rows, int64_t cols, int side) {
-  const int64_t n = rows * cols;
+             int64_t n, int64_t d, int64_t inner) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / cols;
-    out[i] = a[i] * (side ? diag[i - r * cols] : diag[r]);
+    out[i] = a[i] * diag[(i / inner) % d];
   }
 }
 
@@ -392,17 +391,18 @@ extern "C" int t10_permute_dense(int dtype, const void* d_src, void* d_dst, int 
 }
 
 extern "C" int t10_diag_scale(int dtype, const void* d_a, const void* d_diag, void* d_out,
-                              int64_t rows, int64_t cols, int side, t10_stream_t stream) {
+                              int64_t outer, int64_t d, int64_t inner, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t n = rows * cols;
+  T10_REQUIRE(outer >= 0 && d >= 0 && inner >= 0, T10_ERR_INVALID, "diag_scale: negative extent");
+  int64_t n = outer * d * inner;
   if (n == 0) return T10_OK;
   unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
   if (dtype == T10_F64)
     k_diag_scale<double><<<grid, 256, 0, st>>>((const double*)d_a, (const double*)d_diag,
-                                                (double*)d_out, rows, cols, side);
+                                                (double*)d_out, n, d, inner);
   else if (dtype == T10_F32)
     k_diag_scale<float><<<grid, 256, 0, st>>>((const float*)d_a, (const float*)d_diag,
-                                               (float*)d_out, rows, cols, side);
+                                               (float*)d_out, n, d, inner);
   else
     T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "diag_scale: dtype %d", dtype);
   T10_LAUNCH_CHECK();
