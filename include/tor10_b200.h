@@ -163,9 +163,10 @@ typedef struct t10_gemm_problem {
   int32_t lda, ldb, ldc;
 } t10_gemm_problem;
 
-/* Tile decomposition used by t10_ggemm for `tile_cfg`:
- *   0: 64x64xBK16, 4 stages   1: 128x128   2: 128x64   3: 64x64xBK16, 3 stages (3 CTAs/SM)
- *   4: 64x64xBK32, 3 stages   5: 64x64xBK32, 2 stages   100: SIMT cross-check kernel (tests)
+/* Tile decomposition used by t10_ggemm for `tile_cfg` (FP64; all BK = 16):
+ *   0: 64x64, 4 stages   1: 128x128   2: 128x64   3: 64x64, 3 stages, 3 CTAs/SM (default)
+ *   40: 64x64 and 42: 64x128, aligned-only kernel (every lda/ldb/offset even, bases 16-byte aligned)
+ *   100: SIMT cross-check kernel (tests).  FP32 uses the SIMT kernel with 64x64 tiles (cfg 0).
  * t10_ggemm_slots: number of co-resident CTAs of that kernel on the current device (needs CUDA).
  * t10_ggemm_plan_tiles (host only): fills h_tiles [cap,4] = {problem, m0, n0, 0}; call with
  * h_tiles = NULL to size.  With nslots > 0 the tiles are assigned to `nslots` CTA slots by LPT on a
@@ -190,6 +191,8 @@ int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d
 /* Peak-rate probes used by bench.py for the roofline denominators (register-resident loops;
  * mode 1: DMMA, 0: DFMA, 2: DMMA and DFMA warps side by side -- measured 37.0 / 36.5 / 36.8 TF on
  * B200: the two share one FP64 datapath).  Returns achieved TFLOP/s through *tflops.     */
+/* DMMA-only probe with a given number of resident warps per SM sub-partition (1 CTA/SM). */
+int t10_probe_f64_occupancy(int warps_per_scheduler, int iters, double* tflops, t10_stream_t stream);
 int t10_probe_f64_peak(int mode, int iters, double* tflops, t10_stream_t stream);
 
 #ifdef __cplusplus

@@ -1061,12 +1061,13 @@ def _dense_gemm(A2, B2):
         return out
     if K == 0:
         return out.zero_()
-    key = (M, N, K, A2.dtype, A2.device.index)
+    base_ok = (A2.data_ptr() % 16 == 0) and (B2.data_ptr() % 16 == 0)
+    key = (M, N, K, A2.dtype, A2.device.index, base_ok)
     grp = _GEMM_GROUPS.get(key)
     if grp is None:
         prob = np.zeros(1, dtype=_lib.GEMM_PROBLEM_DTYPE)
         prob[0] = (0, 0, 0, M, N, K, K, N, N)
-        grp = _plan.GemmGroup(prob, A2.device, A2.dtype)
+        grp = _plan.GemmGroup(prob, A2.device, A2.dtype, base_aligned=base_ok)
         _GEMM_GROUPS[key] = grp
     grp.run(A2, B2, out)
     return out

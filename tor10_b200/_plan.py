@@ -306,10 +306,14 @@ def pick_tile_cfg(problems):
     return 3
 
 
+ALIGNED_CFGS = (40, 42)   # kernels that require 16-byte aligned operand rows
+FALLBACK_CFG = 3
+
+
 class GemmGroup:
     """Problem table + tile table on the device."""
 
-    def __init__(self, problems, device, dtype, tile_cfg=None):
+    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True):
         lib = _lib.load()
         self.problems = np.ascontiguousarray(problems, dtype=_lib.GEMM_PROBLEM_DTYPE)
         self.nprob = len(self.problems)
@@ -317,15 +321,20 @@ class GemmGroup:
         if tile_cfg is None:
             tile_cfg = pick_tile_cfg(self.problems) if dtype == torch.float64 else 0
         self.tile_cfg = int(tile_cfg)
+        pr = self.problems
+        self.aligned = bool(((pr["lda"] % 2 == 0) & (pr["ldb"] % 2 == 0) & (pr["a_off"] % 2 == 0)
+                             & (pr["b_off"] % 2 == 0)).all()) and bool(base_aligned)
+        if self.tile_cfg in ALIGNED_CFGS and not self.aligned:
+            self.tile_cfg = FALLBACK_CFG      # odd leading dimension somewhere: predicated 8-byte loader kernel
         # CTA slots of the persistent kernel (occupancy query: needs the device) -> LPT slot table
         ns = C.c_int(0)
         with torch.cuda.device(device):
             check(lib.t10_ggemm_slots(self.dtype_code, self.tile_cfg, C.byref(ns)))
         mode = os.environ.get("TOR10_GGEMM_SCHED", "slots")
         f64k = dtype == torch.float64 and self.tile_cfg != 100
-        use_slots = f64k and (mode == "slots" or (mode == "dynamic" and self.tile_cfg >= 10))
+        use_slots = f64k and (mode == "slots" or (mode == "dynamic" and self.tile_cfg in ALIGNED_CFGS))
         self.d_sched = torch.zeros(2, dtype=torch.int32, device=device) \
-            if (f64k and mode == "dynamic" and self.tile_cfg < 10) else None
+            if (f64k and mode == "dynamic" and self.tile_cfg not in ALIGNED_CFGS) else None
         nt = C.c_int64(0)
         check(lib.t10_ggemm_plan_tiles(self.tile_cfg, self.nprob, np_ptr(self.problems), 0, 0, None, None,
                                        C.byref(nt)))
@@ -425,6 +434,15 @@ class ContractPlan:
         self.matched = matched
         sec_a = sorted(set(m[1] for m in matched))
         sec_b = sorted(set(m[2] for m in matched))
+        want_aligned = a.dtype == torch.float64 and pick_tile_cfg(None) in ALIGNED_CFGS
+        if want_aligned:
+            # an operand read in place has leading dimension = its sector width; odd widths would force the
+            # whole group onto the predicated-loader kernel, so such an operand is copied once into the padded
+            # scratch layout by the relayout kernel (identity permutation)
+            if ident_a and any(int(La.cols[s]) % 2 for s in sec_a):
+                ident_a = False
+            if ident_b and any(int(Lb.cols[s]) % 2 for s in sec_b):
+                ident_b = False
         self.rel_a = None if ident_a else get_relayout(Ma, La, map_a, padded=True, sectors=sec_a)
         self.rel_b = None if ident_b else get_relayout(Mb, Lb, map_b, padded=True, sectors=sec_b)
         pa = self.rel_a.packed if self.rel_a else PackedLayout.native(La)

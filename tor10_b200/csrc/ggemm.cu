@@ -291,77 +291,34 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
   }
 }
 
-// ------------------------------------------------------------------ FP64 DMMA, warp-specialised
-// One producer warp issues every cp.async of the CTA (per-lane row pointers set up once per tile, three
-// instructions per 16-byte chunk) and signals "stage full" through an mbarrier
-// (cp.async.mbarrier.arrive.noinc); the consumer warps run nothing but LDS.64 + DMMA and hand stages
-// back through an "empty" mbarrier.  No __syncthreads in the main loop, the pipeline state runs on
-// across tile boundaries (the producer prefetches the next tile while the consumers drain the current
-// one), and ragged tiles run a compute body specialised on the number of valid 8x8 fragments.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(a), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) {
-  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
-}
-
-template <class Cfg, int MI_V, int NI_V>
-__device__ __forceinline__ void ws_compute(const double* __restrict__ as, const double* __restrict__ bs,
-                                           double (&acc)[Cfg::MI][Cfg::NI][2]) {
-#pragma unroll
-  for (int kk = 0; kk < Cfg::BK; kk += 4) {
-    double af[MI_V], bf[NI_V];
-#pragma unroll
-    for (int i = 0; i < MI_V; ++i) af[i] = as[i * 8 * Cfg::LDA + kk];
-#pragma unroll
-    for (int j = 0; j < NI_V; ++j) bf[j] = bs[kk * Cfg::LDB + j * 8];
-#pragma unroll
-    for (int i = 0; i < MI_V; ++i)
-#pragma unroll
-      for (int j = 0; j < NI_V; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-  }
-}
-
-template <class Cfg, int MIN_CTAS, bool RAGGED>
-__global__ void __launch_bounds__(Cfg::THREADS + 32, MIN_CTAS)
-k_ggemm_f64_ws(const double* __restrict__ Abase, const double* __restrict__ Bbase,
-               double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob, int64_t ntiles,
-               const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start) {
-  static_assert(Cfg::MI == 4 && Cfg::NI == 4, "ragged dispatch below assumes 32x32 warp tiles");
+// ------------------------------------------------------------------ FP64 DMMA, aligned-only lean kernel
+// Main loop organised like CUTLASS's multistage mainloop (the kernel cuBLAS runs for FP64 on this chip):
+// register double-buffered fragments, the next k-group's LDS issued BEFORE the current group's DMMAs, the
+// cp.asyncs of the stage being prefetched spread over the first three k-groups, the single wait+barrier
+// of a k-step placed before its last group.  ONE loader: every operand row start is 16-byte aligned
+// (host-checked), M/N edges are clamped, the K tail is zero-filled through the cp.async src-size operand
+// in the same instruction stream (no second code path, no spills).  Used whenever every problem of the group has even lda/ldb and
+// even operand offsets; other groups run k_ggemm_f64.
+template <class Cfg, int MIN_CTAS>
+__global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
+k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbase,
+               double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
+               int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start) {
+  static_assert(Cfg::BK == 16, "four k-groups per stage");
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(Bs + Cfg::STAGES * Cfg::B_STAGE);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  constexpr int NCW = Cfg::THREADS / 32;  // consumer warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 32);    // every producer lane arrives when its cp.asyncs have landed
-      mbar_init(&empty_bar[s], NCW);  // one arrival per consumer warp
-    }
-  }
-  __syncthreads();
+  const int g = lane >> 2, tig = lane & 3;
+  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
+  constexpr int A_PASSES = (Cfg::BM * (Cfg::BK / 2)) / Cfg::THREADS;
+  constexpr int B_PASSES = (Cfg::BK * (Cfg::BN / 2)) / Cfg::THREADS;
+  constexpr int A_RPP = Cfg::THREADS / (Cfg::BK / 2), B_RPP = Cfg::THREADS / (Cfg::BN / 2);
+  constexpr int NPASS = A_PASSES + B_PASSES;
+  const int ar0 = threadIdx.x / (Cfg::BK / 2), akc = (threadIdx.x % (Cfg::BK / 2)) * 2;
+  const int br0 = threadIdx.x / (Cfg::BN / 2), bnc = (threadIdx.x % (Cfg::BN / 2)) * 2;
+  const unsigned sa0 = (unsigned)__cvta_generic_to_shared(As + ar0 * Cfg::LDA + akc);
+  const unsigned sb0 = (unsigned)__cvta_generic_to_shared(Bs + br0 * Cfg::LDB + bnc);
 
   int64_t t_beg = blockIdx.x, t_end = ntiles, t_step = gridDim.x;
   if (slot_start != nullptr) {
@@ -369,86 +326,20 @@ k_ggemm_f64_ws(const double* __restrict__ Abase, const double* __restrict__ Bbas
     t_end = slot_start[blockIdx.x + 1];
     t_step = 1;
   }
-  int stage = 0;
-  unsigned phase = 0;
-
-  if (warp == NCW) {
-    // ================================ producer warp =====================================
-    // A tile: BM x BK, 16-byte chunks: lane owns k-chunk (lane % 8 [%16 for BK=32]) of rows lane/CPR + i*RPI
-    constexpr int CPR_A = Cfg::BK / 2;            // chunks per A row
-    constexpr int RPI_A = 32 / CPR_A;             // rows covered per pass
-    constexpr int NPASS_A = Cfg::BM / RPI_A;
-    // B tile: BK x BN: lane owns column chunk lane + 32*j of every k row
-    constexpr int CPR_B = Cfg::BN / 2;
-    constexpr int NCH_B = CPR_B / 32;             // chunks per lane per row
-    for (int64_t t = t_beg; t < t_end; t += t_step) {
-      const int4 tile = tiles[t];
-      const t10_gemm_problem p = prob[tile.x];
-      const int m0 = tile.y, n0 = tile.z;
-      const int m_rem = p.m - m0, n_rem = p.n - n0;
-      const bool a16 = ((p.lda & 1) == 0) && ((p.a_off & 1) == 0) && (((uintptr_t)Abase & 15) == 0);
-      const bool b16 = ((p.ldb & 1) == 0) && (((p.b_off + n0) & 1) == 0) && (((uintptr_t)Bbase & 15) == 0);
-      const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
-      const int a_kc = (lane % CPR_A) * 2, a_r0 = lane / CPR_A;
-      const double* a_ptr = Abase + p.a_off + (int64_t)(m0 + a_r0) * p.lda + a_kc;
-      const int64_t a_step = (int64_t)RPI_A * p.lda;
-      const double* b_ptr = Bbase + p.b_off + n0 + lane * 2;
-      for (int kt = 0; kt < KT; ++kt) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int k0 = kt * Cfg::BK;
-        double* as = As + stage * Cfg::A_STAGE + a_r0 * Cfg::LDA + a_kc;
-        const int a_kvalid = max(0, min(2, p.k - k0 - a_kc));  // doubles of this chunk inside K
-#pragma unroll
-        for (int i = 0; i < NPASS_A; ++i) {
-          const int valid = (a_r0 + i * RPI_A < m_rem) ? a_kvalid : 0;
-          const double* g = valid ? a_ptr + i * a_step + k0 : Abase;
-          double* sdst = as + i * RPI_A * Cfg::LDA;
-          if (a16) {
-            cp_async16(sdst, g, valid * 8);
-          } else {
-            cp_async8(sdst, g, valid >= 1 ? 8 : 0);
-            cp_async8(sdst + 1, valid >= 2 ? g + 1 : Abase, valid >= 2 ? 8 : 0);
-          }
-        }
-        double* bsm = Bs + stage * Cfg::B_STAGE + lane * 2;
-        const int k_rows = min(Cfg::BK, p.k - k0);
-#pragma unroll
-        for (int r = 0; r < Cfg::BK; ++r) {
-#pragma unroll
-          for (int j = 0; j < NCH_B; ++j) {
-            const int nc = lane * 2 + j * 64;
-            const int valid = (r < k_rows) ? max(0, min(2, n_rem - nc)) : 0;
-            const double* g = valid ? b_ptr + (int64_t)(k0 + r) * p.ldb + j * 64 : Bbase;
-            double* sdst = bsm + r * Cfg::LDB + j * 64;
-            if (b16) {
-              cp_async16(sdst, g, valid * 8);
-            } else {
-              cp_async8(sdst, g, valid >= 1 ? 8 : 0);
-              cp_async8(sdst + 1, valid >= 2 ? g + 1 : Bbase, valid >= 2 ? 8 : 0);
-            }
-          }
-        }
-        mbar_arrive_cp_async(&full_bar[stage]);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-    cp_async_wait<0>();
-    asm volatile("cp.async.wait_all;\n" ::);
-    return;
-  }
-
-  // ================================== consumer warps =====================================
-  const int g = lane >> 2, tig = lane & 3;
-  const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
   for (int64_t t = t_beg; t < t_end; t += t_step) {
     const int4 tile = tiles[t];
     const t10_gemm_problem p = prob[tile.x];
     const int m0 = tile.y, n0 = tile.z;
     const int m_rem = p.m - m0, n_rem = p.n - n0;
     const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
-    const int mi_valid = max(0, min(Cfg::MI, (m_rem - wm0 + 7) >> 3));
-    const int ni_valid = max(0, min(Cfg::NI, (n_rem - wn0 + 7) >> 3));
-    const int vcode = (mi_valid == 0 || ni_valid == 0) ? 0 : (RAGGED ? mi_valid * 4 + ni_valid : 20);
+    const bool active = (m_rem > wm0) && (n_rem > wn0);
+    // per-thread source pointers; rows beyond m and column chunks beyond n are clamped (never stored)
+    const double* pa[A_PASSES];
+#pragma unroll
+    for (int i = 0; i < A_PASSES; ++i)
+      pa[i] = Abase + p.a_off + (int64_t)(m0 + min(ar0 + i * A_RPP, m_rem - 1)) * p.lda + akc;
+    const double* pb = Bbase + p.b_off + n0 + min(bnc, ((n_rem - 1) >> 1) << 1) + (int64_t)br0 * p.ldb;
+    const int64_t b_pass = (int64_t)B_RPP * p.ldb, b_kstep = (int64_t)Cfg::BK * p.ldb;
 
     double acc[Cfg::MI][Cfg::NI][2];
 #pragma unroll
@@ -456,26 +347,71 @@ k_ggemm_f64_ws(const double* __restrict__ Abase, const double* __restrict__ Bbas
 #pragma unroll
       for (int j = 0; j < Cfg::NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = 0; kt < KT; ++kt) {
-      mbar_wait(&full_bar[stage], phase);
-      const double* as = As + stage * Cfg::A_STAGE + (wm0 + g) * Cfg::LDA + tig;
-      const double* bs = Bs + stage * Cfg::B_STAGE + tig * Cfg::LDB + wn0 + g;
-      switch (vcode) {
-#define T10_WS_CASE(MV, NV) \
-  case MV * 4 + NV: ws_compute<Cfg, MV, NV>(as, bs, acc); break;
-        T10_WS_CASE(4, 4) T10_WS_CASE(4, 3) T10_WS_CASE(4, 2) T10_WS_CASE(4, 1)
-        T10_WS_CASE(3, 4) T10_WS_CASE(3, 3) T10_WS_CASE(3, 2) T10_WS_CASE(3, 1)
-        T10_WS_CASE(2, 4) T10_WS_CASE(2, 3) T10_WS_CASE(2, 2) T10_WS_CASE(2, 1)
-        T10_WS_CASE(1, 4) T10_WS_CASE(1, 3) T10_WS_CASE(1, 2) T10_WS_CASE(1, 1)
-#undef T10_WS_CASE
-        default: break;  // this warp's 32x32 patch lies outside the sector
+    // passes [lo, hi) of stage kt; k validity through the src-size operand (zero fill)
+    auto issue = [&](int kt, int lo, int hi) {
+      const int k0 = kt * Cfg::BK;
+      const unsigned so_a = (unsigned)((kt % Cfg::STAGES) * Cfg::A_STAGE * 8);
+      const unsigned so_b = (unsigned)((kt % Cfg::STAGES) * Cfg::B_STAGE * 8);
+      const int a_bytes = max(0, min(2, p.k - k0 - akc)) * 8;
+#pragma unroll
+      for (int q = 0; q < NPASS; ++q) {
+        if (q < lo || q >= hi) continue;
+        if (q < A_PASSES) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa0 + so_a + q * A_RPP * Cfg::LDA * 8),
+                       "l"(a_bytes ? pa[q] + k0 : Abase), "r"(a_bytes));
+        } else {
+          const int i = q - A_PASSES;
+          const int b_bytes = (k0 + br0 + i * B_RPP < p.k) ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sb0 + so_b + i * B_RPP * Cfg::LDB * 8),
+                       "l"(b_bytes ? pb + (int64_t)kt * b_kstep + i * b_pass : Bbase), "r"(b_bytes));
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-    }
+    };
 
-    if (vcode == 0) continue;
+    __syncthreads();  // previous tile's stages free
+#pragma unroll
+    for (int s2 = 0; s2 < Cfg::STAGES - 1; ++s2) {
+      if (s2 < KT) issue(s2, 0, NPASS);
+      cp_async_commit();
+    }
+    cp_async_wait<Cfg::STAGES - 2>();
+    __syncthreads();
+
+    double af[2][Cfg::MI], bf[2][Cfg::NI];
+    auto load_frags = [&](int kt, int grp, int buf) {
+      const double* as = As + (kt % Cfg::STAGES) * Cfg::A_STAGE + (wm0 + g) * Cfg::LDA + tig + grp * 4;
+      const double* bs = Bs + (kt % Cfg::STAGES) * Cfg::B_STAGE + (tig + grp * 4) * Cfg::LDB + wn0 + g;
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) af[buf][i] = as[i * 8 * Cfg::LDA];
+#pragma unroll
+      for (int j = 0; j < Cfg::NI; ++j) bf[buf][j] = bs[j * 8];
+    };
+    if (KT > 0) load_frags(0, 0, 0);
+
+    for (int kt = 0; kt < KT; ++kt) {
+      const int nk = kt + Cfg::STAGES - 1;
+#pragma unroll
+      for (int grp = 0; grp < 4; ++grp) {
+        if (grp < 3) load_frags(kt, grp + 1, (grp + 1) & 1);
+        else if (kt + 1 < KT) load_frags(kt + 1, 0, 0);
+        if (grp < 3 && nk < KT) issue(nk, grp * NPASS / 3, (grp + 1) * NPASS / 3);
+        if (grp == 2) {
+          cp_async_commit();
+          cp_async_wait<Cfg::STAGES - 2>();
+          __syncthreads();
+        }
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+            for (int j = 0; j < Cfg::NI; ++j)
+              dmma884(acc[i][j][0], acc[i][j][1], af[grp & 1][i], bf[grp & 1][j]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+
+    if (!active) continue;
     double* C = Cbase + p.c_off;
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
 #pragma unroll
@@ -624,12 +560,11 @@ __global__ void k_probe_mixed(double* out, int iters) {
   if (s == 123.456) out[0] = s;
 }
 
-using CfgA = F64Cfg<64, 64, 32, 32, 4>;       // tile_cfg 0: 128 thr, 75.8 KB smem, 2 CTAs/SM
+using CfgA = F64Cfg<64, 64, 32, 32, 4>;       // tile_cfg 0 / 40: 128 thr, 75.8 KB smem, 2 CTAs/SM
 using CfgB = F64Cfg<128, 128, 64, 32, 4>;     // tile_cfg 1: 256 thr, 149.5 KB smem
 using CfgC = F64Cfg<128, 64, 64, 32, 4>;      // tile_cfg 2: 128 thr, 116.7 KB smem
-using CfgD = F64Cfg<64, 64, 32, 32, 3>;       // tile_cfg 3: 128 thr, 56.8 KB smem, 3 CTAs/SM
-using CfgE = F64Cfg<64, 64, 32, 32, 3, 32>;   // tile_cfg 4: BK = 32, 107.5 KB smem, 2 CTAs/SM
-using CfgF = F64Cfg<64, 64, 32, 32, 2, 32>;   // tile_cfg 5: BK = 32, 2 stages, 71.7 KB smem, 3 CTAs/SM
+using CfgD = F64Cfg<64, 64, 32, 32, 3>;       // tile_cfg 3: 128 thr, 56.8 KB smem, 3 CTAs/SM (default)
+using CfgL = F64Cfg<64, 128, 32, 64, 3>;      // tile_cfg 42: cuBLAS's large-GEMM shape, 128 thr, 82.9 KB
 
 // launch == false: only report the number of resident CTA slots (sm_count x CTAs/SM)
 template <class Cfg, int MIN_CTAS, bool RAGGED = true>
@@ -661,19 +596,16 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
   return T10_OK;
 }
 
-template <class Cfg, int MIN_CTAS, bool RAGGED = true>
-static int launch_f64_ws(bool launch, int* nslots_out, const double* A, const double* B, double* C,
+template <class Cfg, int MIN_CTAS>
+static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const double* B, double* C,
                          const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
-                         const int32_t* slot_start, int32_t* /*sched: the ws kernel keeps static schedules*/,
-                         cudaStream_t st) {
-  auto kern = k_ggemm_f64_ws<Cfg, MIN_CTAS, RAGGED>;
-  constexpr int SMEM = Cfg::SMEM_BYTES + 2 * Cfg::STAGES * 8;
-  constexpr int THREADS = Cfg::THREADS + 32;
+                         const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st) {
+  auto kern = k_ggemm_f64_v5<Cfg, MIN_CTAS>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     int occ = 0;
-    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, SMEM));
+    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
     ctas_per_sm = occ;
   }
@@ -681,6 +613,8 @@ static int launch_f64_ws(bool launch, int* nslots_out, const double* A, const do
     *nslots_out = sm_count() * ctas_per_sm;
     return T10_OK;
   }
+  T10_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, T10_ERR_INVALID,
+              "aligned ggemm kernel: operand base pointers must be 16-byte aligned");
   unsigned grid;
   if (slot_start != nullptr) {
     T10_REQUIRE(nslots >= 1, T10_ERR_INVALID, "slot table without slots");
@@ -688,7 +622,7 @@ static int launch_f64_ws(bool launch, int* nslots_out, const double* A, const do
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, THREADS, SMEM, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -701,25 +635,19 @@ static int dispatch_f64(int tile_cfg, bool launch, int* nslots_out, const double
     case 1: return launch_f64<CfgB, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
     case 2: return launch_f64<CfgC, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
     case 3: return launch_f64<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 4: return launch_f64<CfgE, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 5: return launch_f64<CfgF, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 10: return launch_f64_ws<CfgA, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 11: return launch_f64_ws<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 12: return launch_f64_ws<CfgE, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 13: return launch_f64_ws<CfgD, 4>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 14: return launch_f64_ws<CfgA, 3, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 6: return launch_f64<CfgA, 2, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 7: return launch_f64<CfgD, 3, false>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 40: return launch_f64_v5<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 42: return launch_f64_v5<CfgL, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
     default: T10_REQUIRE(false, T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
   }
 }
 
 static bool tile_dims(int cfg, int* bm, int* bn, int* bk) {
+  *bk = 16;
   switch (cfg) {
-    case 0: case 3: case 6: case 7: case 10: case 11: case 13: case 14: case 100: *bm = 64; *bn = 64; *bk = 16; return true;
-    case 4: case 5: case 12: *bm = 64; *bn = 64; *bk = 32; return true;
-    case 1: *bm = 128; *bn = 128; *bk = 16; return true;
-    case 2: *bm = 128; *bn = 64; *bk = 16; return true;
+    case 0: case 3: case 40: case 100: *bm = 64; *bn = 64; return true;
+    case 1: *bm = 128; *bn = 128; return true;
+    case 2: *bm = 128; *bn = 64; return true;
+    case 42: *bm = 64; *bn = 128; return true;
     default: return false;
   }
 }
@@ -825,6 +753,32 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
     T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "ggemm: dtype %d not supported", dtype);
   }
   T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+extern "C" int t10_probe_f64_occupancy(int warps_per_scheduler, int iters, double* tflops, t10_stream_t stream) {
+  // DMMA-only probe with exactly `warps_per_scheduler` resident warps on every SM sub-partition
+  cudaStream_t st = (cudaStream_t)stream;
+  T10_REQUIRE(warps_per_scheduler >= 1 && warps_per_scheduler <= 16, T10_ERR_INVALID, "1..16 warps");
+  double* d_out;
+  T10_CUDA(cudaMalloc(&d_out, 8));
+  cudaEvent_t e0, e1;
+  T10_CUDA(cudaEventCreate(&e0));
+  T10_CUDA(cudaEventCreate(&e1));
+  const int blocks = sm_count(), threads = 128 * warps_per_scheduler;  // one CTA per SM
+  for (int rep = 0; rep < 2; ++rep) {
+    T10_CUDA(cudaEventRecord(e0, st));
+    k_probe_dmma<<<blocks, threads, 0, st>>>(d_out, iters);
+    T10_CUDA(cudaEventRecord(e1, st));
+    T10_CUDA(cudaEventSynchronize(e1));
+  }
+  float ms = 0;
+  T10_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  double warps = (double)blocks * threads / 32.0;
+  *tflops = 2.0 * warps * (double)iters * 16.0 * 256.0 / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
   return T10_OK;
 }
 

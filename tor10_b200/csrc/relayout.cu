@@ -76,20 +76,20 @@ k_relayout_blocks(const T* __restrict__ src, T* __restrict__ dst, int32_t* __res
         if (ok) addr[u] = base + co;
       }
     }
-    if (EMIT) {  // plan time: record the source element index of every destination element
+    if constexpr (EMIT) {  // plan time: record the source element index of every destination element
       int32_t* out = emit + tile.dst + tc;
 #pragma unroll
       for (int u = 0; u < RL_ROWS_PER_THREAD; ++u)
         if (rbeg + u < rend) out[(int64_t)(rbeg + u) * tile.dld] = (int32_t)addr[u];
-      continue;
+    } else {
+      T v[RL_ROWS_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < RL_ROWS_PER_THREAD; ++u) v[u] = addr[u] >= 0 ? src[addr[u]] : T(0);
+      T* out = dst + tile.dst + tc;
+#pragma unroll
+      for (int u = 0; u < RL_ROWS_PER_THREAD; ++u)
+        if (rbeg + u < rend) out[(int64_t)(rbeg + u) * tile.dld] = v[u];
     }
-    T v[RL_ROWS_PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < RL_ROWS_PER_THREAD; ++u) v[u] = addr[u] >= 0 ? src[addr[u]] : T(0);
-    T* out = dst + tile.dst + tc;
-#pragma unroll
-    for (int u = 0; u < RL_ROWS_PER_THREAD; ++u)
-      if (rbeg + u < rend) out[(int64_t)(rbeg + u) * tile.dld] = v[u];
   }
 }
 
