@@ -356,6 +356,24 @@ def test_dense_permute_kernel(T):
             assert torch.equal(c.Storage, x.permute(*perm).contiguous())
 
 
+def test_dense_permute_tma_path(T, monkeypatch):
+    """Permutes that keep the innermost bond go through the TMA load/store ring (UTMALDG/UTMASTG); ragged
+    extents exercise the hardware edge clipping.  Bit-exact against torch's strided copy."""
+    monkeypatch.setenv("TOR10_PERMUTE_TMA_MIN_BYTES", "0")
+    g = torch.Generator().manual_seed(5)
+    cases = [((1024, 2, 2, 1024), (0, 2, 1, 3)), ((37, 5, 3, 130), (2, 0, 1, 3)), ((300, 7, 258), (1, 0, 2)),
+             ((9, 4, 6, 5, 64), (3, 1, 0, 2, 4)), ((513, 3, 1026), (1, 0, 2)), ((2, 3, 4, 5, 6, 8), (4, 2, 0, 3, 1, 5))]
+    for shape, perm in cases:
+        for dt in (torch.float64, torch.float32):
+            x = torch.rand(shape, generator=g, dtype=dt).to(DEV)
+            got = T.UniTensor._contiguous_dense(x.permute(*perm))
+            assert got.is_contiguous() and torch.equal(got, x.permute(*perm).contiguous())
+    # sliced (non-zero offset, strided) source
+    x = torch.rand((64, 6, 512), generator=g, dtype=torch.float64).to(DEV)
+    v = x[:, 1:5, 128:384].permute(1, 0, 2)
+    assert torch.equal(T.UniTensor._contiguous_dense(v), v.contiguous())
+
+
 def test_matmul_goldens(T, golden):
     z, _ = golden("dense")
     mats = [_pdense(T, {"dims": [m, k], "labels": [0, 1], "rowrank": 1, "seed": 600 + j})

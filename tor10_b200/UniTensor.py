@@ -194,6 +194,11 @@ class UniTensor:
         self._inv_mapper = np.zeros(len(self._mapper), dtype=np.int64)
         self._inv_mapper[self._mapper] = rng
 
+    def _layout_current(self):
+        """True when the arena is laid out for the CURRENT bond order and row/col split.  The reference only
+        tracks the bond order (`_contiguous`, quirk Q1); here a changed rowrank also counts as "needs relayout"."""
+        return self._contiguous and self.rowrank == self._layout.rowrank
+
     def _logical_layout(self):
         return _plan.get_layout(list(self.bonds), self.braket, self.rowrank, self._arena.device)
 
@@ -263,7 +268,7 @@ class UniTensor:
         if not self.is_symm:
             return None
         if self._bq is None:
-            lay = self._layout if self._contiguous and self.rowrank == self._layout.rowrank else self._logical_layout()
+            lay = self._layout if self._layout_current() else self._logical_layout()
             self._bq = lay.block_qnums
         return self._bq
 
@@ -491,7 +496,7 @@ class UniTensor:
             print("braket_form : %s" % ("True" if self.is_braket else "False"))
         if self.is_symm:
             print("[Symmetry]")
-            src = self if self._contiguous else self.Contiguous()
+            src = self if self._layout_current() else self.Contiguous()
             for b in range(len(src.Storage)):
                 print(src.Storage[b])
         else:
@@ -704,7 +709,7 @@ class UniTensor:
     def Contiguous_(self):
         """UniTensor.py:2016-2059"""
         if self.is_symm:
-            if self._contiguous:
+            if self._layout_current():
                 return self
             out = self.Contiguous()
             out.name = self.name
@@ -717,7 +722,7 @@ class UniTensor:
         """UniTensor.py:2061-2145.  Symmetric: one launch of the family-2 block relayout kernel (the
         reference runs a Python loop over every stored element, :2108-2129)."""
         if self.is_symm:
-            if self._contiguous:
+            if self._layout_current():
                 return self
             L = self._logical_layout()
             plan = _plan.get_relayout(self._layout, L, self._mapper, padded=False)
@@ -747,7 +752,7 @@ class UniTensor:
 
     def is_contiguous(self):
         if self.is_symm:
-            return self._contiguous
+            return self._layout_current()
         return self._dense.is_contiguous()
 
     def Permute(self, mapper, rowrank=None, by_label=False):
@@ -921,7 +926,7 @@ class UniTensor:
         if block.is_symm or block.is_diag or len(block.bonds) != 2:
             raise TypeError("UniTensor.PutBlock", "[ERROR] the block must be a dense rank-2 UniTensor")
         s = self._find_block(qnum, "UniTensor.PutBlock")
-        if self._contiguous:
+        if self._layout_current():
             dst = self._layout.views(self._arena_tensor())[s]
             if tuple(dst.shape) != tuple(block._dense.shape):
                 raise TypeError("UniTensor.PutBlock", "[ERROR] the input block does not match the shape %s of the "
@@ -957,7 +962,7 @@ class UniTensor:
             out._mac(torch_tensor=x.reshape(r, -1))
             return out
         s = self._find_block(qnum, "UniTensor.GetBlock")
-        if self._contiguous:
+        if self._layout_current():
             blk = self._layout.views(self._arena_tensor())[s].clone()
         else:
             # gather only this sector through the relayout kernel (reference: per-element loop :3255-3273)

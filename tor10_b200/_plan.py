@@ -395,7 +395,12 @@ class ContractPlan:
         if self.out_rowrank < 1 or self.out_rowrank >= len(self.out_bonds):
             raise TypeError("UniTensor.__init__", "[ERROR] tensor with symmetry must have at least one rank for "
                                                   "row space and one rank for column space")
-        Lo = get_layout(self.out_bonds, self.out_braket, self.out_rowrank, dev)
+        # The GEMMs produce the result split as (a's free bonds | b's free bonds).  When the inferred rowrank
+        # differs (outside the reference's well-defined domain: there it raises inside torch.matmul or stores
+        # wrong-shaped blocks, quirk Q2) the result is returned in that memory layout with the reference's
+        # metadata (labels, bonds, inferred rowrank); reading it relayouts like any permuted tensor.
+        self.mem_rowrank = rr_a
+        Lo = get_layout(self.out_bonds, self.out_braket, self.mem_rowrank, dev)
         self.La, self.Lb, self.Lo = La, Lb, Lo
         # the reference tests only `_mapper == identity` (quirk Q1); a changed rowrank with identity
         # mapper leaves its Storage stale.  Here the relayout runs whenever the memory layout differs.
@@ -409,10 +414,9 @@ class ContractPlan:
             if ab is not None and bb is not None:
                 ma, ka, kb, nb = int(La.rows[ab]), int(La.cols[ab]), int(Lb.rows[bb]), int(Lb.cols[bb])
                 if ka != kb or ma != int(Lo.rows[ob]) or nb != int(Lo.cols[ob]):
-                    # outside the well-defined domain (quirk Q2): the reference raises inside torch.matmul
-                    # or silently stores a block of the wrong shape
+                    # contracted bonds whose charge tables differ (the reference never compares them, quirk Q4)
                     raise RuntimeError("Contract(a,b): sector %s has mismatched block shapes A[%d,%d] B[%d,%d] "
-                                       "out[%d,%d] (row/col split of the result differs from the operands')"
+                                       "out[%d,%d] (the contracted bonds of a and b carry different charges)"
                                        % (Lo.block_qnums[ob].tolist(), ma, ka, kb, nb, Lo.rows[ob], Lo.cols[ob]))
                 matched.append((ob, ab, bb))
         self.all_matched = len(matched) == Lo.nsec
@@ -472,7 +476,12 @@ class ContractPlan:
             if self.shard is not None and self.shard[1] > 1:
                 from .parallel import gather_ranges
                 gather_ranges(Cc, self.ranges, self.shard[0])
-        return UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.out_rowrank, self.Lo, Cc)
+        out = UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.mem_rowrank, self.Lo, Cc)
+        if self.out_rowrank != self.mem_rowrank:
+            out.rowrank = self.out_rowrank
+            out._bq = None
+            out._check_braket()
+        return out
 
 
 def contract_key(a, b):

@@ -237,11 +237,17 @@ k_diag_scale(const T* __restrict__ a, const T* __restrict__ diag, T* __restrict_
   }
 }
 
+// permute_tma.cu: TMA load + TMA store ring; T10_ERR_UNSUPPORTED when the shape is not eligible
+int permute_dense_tma(int dtype, const void* src, void* dst, int rank, const int64_t* shape,
+                      const int64_t* sstride, cudaStream_t st);
+
 template <typename T>
 static int launch_permute(const T* src, T* dst, const PermDesc& pd, cudaStream_t st) {
   const int last = pd.rank - 1;
   const int grid_cap = sm_count() * 8;
   if (pd.sstride[last] == 1) {
+    int rc = permute_dense_tma(sizeof(T) == 8 ? T10_F64 : T10_F32, src, dst, pd.rank, pd.shape, pd.sstride, st);
+    if (rc != T10_ERR_UNSUPPORTED) return rc;
     // row copy; widest vector that divides the row, all source strides and both pointers
     int vec = (int)(16 / sizeof(T));
     auto ok = [&](int v) {

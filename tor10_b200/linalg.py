@@ -172,11 +172,12 @@ def Qdr(a):
 
 def _svd(a, keepdim, who):
     _check_rank2(a, who)
-    # torch.svd(some=True) of the reference == linalg.svd(full_matrices=False) with V = Vh^T.  On the device
-    # the cuSOLVER driver is chosen explicitly: gesvda measured 1.7x (64x64) to 8x (1024x1024) faster than
-    # torch's default gesvdj on B200 with a smaller reconstruction error (tools/svd_drivers.py).
+    # torch.svd(some=True) of the reference == linalg.svd(full_matrices=False) with V = Vh^T.  Default cuSOLVER
+    # driver = torch's (gesvdj with gesvd fallback).  TOR10_SVD_DRIVER=gesvda is 1.7x (64x64) to 8x (1024x1024)
+    # faster on B200 (tools/svd_drivers.py) but fails to converge on rank-deficient sector blocks and shifts
+    # the iTEBD energy trajectory by 3e-9, so it is opt-in.
     x = a._dense
-    drv = os.environ.get("TOR10_SVD_DRIVER", "gesvda") if x.device.type == "cuda" else None
+    drv = os.environ.get("TOR10_SVD_DRIVER") if x.device.type == "cuda" else None
     u, s, vh = torch.linalg.svd(x, full_matrices=False, driver=drv or None)
     tmp = _new_label(a)
     if keepdim is not None:
