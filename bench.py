@@ -173,7 +173,7 @@ def main():
     from tor10_b200 import _plan, parallel
 
     if world > 1:
-        parallel.enable()
+        parallel.enable(transport=os.environ.get("TOR10_GATHER", "auto"))
     A, B = c3a_specs(args.chi)
     a = psym(T, A, seed=1003, device=dev)
     b = psym(T, B, seed=1004, device=dev)
@@ -227,6 +227,20 @@ def main():
         ms_total = ms_local
     ms_per_step = ms_total / args.steps
     value = flops / (ms_per_step * 1e-3) / 1e9
+
+    # ---- the same step with results left sharded (every rank keeps only its own sectors: no collective) ----
+    sharded_ms = None
+    if world > 1:
+        parallel.enable(transport="none")
+        for _ in range(3):
+            step()
+        barrier()
+        ts = float(np.sum(timed_loop(step, args.steps)))
+        tt = torch.tensor([ts], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sharded_ms = float(tt.item()) / args.steps
+        parallel.enable(transport=os.environ.get("TOR10_GATHER", "auto"))
+        plan = _plan.get_contract_plan(a, b)
 
     # ---- stage timings on this rank's share (roofline of the dominant kernel) ---------------
     A_arena, B_arena = a._arena_tensor(), b._arena_tensor()
@@ -312,7 +326,11 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "sectors": int(plan.Lo.nsec), "algorithmic_gflop": flops / 1e9,
                    "nnz_per_operand": int(a._layout.nnz), "tile_cfg": plan.gemm.tile_cfg,
-                   "parallelism": "sectors sharded over %d GPU(s), NCCL gather" % world if world > 1 else "1 GPU",
+                   "parallelism": ("sectors sharded over %d GPUs (contiguous runs balanced by flops); result gathered "
+                                   "on every rank: %s" % (world, {"p2p": "symmetric-memory staging + device barrier + one "
+                                   "pull kernel over NVLink peer memory", "nccl": "NCCL all_gather_into_tensor"}.get(
+                                       parallel.transport_for(), parallel.transport_for()))) if world > 1 else "1 GPU",
+                   "value_if_result_stays_sharded_gflops": (flops / (sharded_ms * 1e-3) / 1e9) if sharded_ms else None,
                    "l2": "flushed between steps (256 MiB write); every step timed by its own CUDA event pair",
                    "plan": "cached (block maps, relayout tables, tile table built once outside the timed region)"},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,

@@ -142,6 +142,13 @@ int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntile
 int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_index,
                        t10_stream_t stream);
 
+/* Multi-GPU sector gather over NVLink peer memory (no reference counterpart: the reference has no
+ * multi-device code).  dst[lo_i .. hi_i) = src_i[lo_i .. hi_i) for nseg <= 16 slices, where src_i are
+ * peer-mapped (symmetric-memory) staging buffers of the other ranks; bounds multiples of 16 bytes.
+ * One launch pulls from all peers at once.                                                 */
+int t10_gather_peers(int dtype, void* d_dst, int nseg, const void* const* h_src, const int64_t* h_lo,
+                     const int64_t* h_hi, t10_stream_t stream);
+
 /* Dense strided permute: dst (contiguous, shape = h_shape) [i0..i_{r-1}] =
  * src[sum_k i_k * h_src_strides[k]]  (strides in elements).                            */
 int t10_permute_dense(int dtype, const void* d_src, void* d_dst, int rank,

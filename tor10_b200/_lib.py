@@ -62,6 +62,7 @@ SIGNATURES = {
     "t10_relayout_tables": [_l, _i, _p, _p, _p, _p, _p, _p, _p],
     "t10_relayout_blocks": [_i, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "t10_relayout_index": [_i, _p, _p, _l, _p, _p],
+    "t10_gather_peers": [_i, _p, _i, _p, _p, _p, _p],
     "t10_permute_dense": [_i, _p, _p, _i, _p, _p, _p],
     "t10_diag_scale": [_i, _p, _p, _p, _l, _l, _l, _p],
     "t10_ggemm_tile_shape": [_i, _p, _p],

@@ -367,6 +367,10 @@ class ContractPlan:
         from .Bond import BondType, BD_KET
         STATS["contract_build"] += 1
         self.shard = shard
+        self._transport, self._stage = None, None
+        if shard is not None:
+            from . import parallel
+            self._transport = parallel.transport_for()
         same, a_ind, b_ind, a_free, b_free = label_match(a.labels, b.labels)
         if len(same) == 0:
             raise Exception("Developing")                                          # :3745-3747 (Q6)
@@ -471,11 +475,22 @@ class ContractPlan:
                 A = self.rel_a.run(A, torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt))
             if self.rel_b is not None:
                 B = self.rel_b.run(B, torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt))
-            Cc = self.Lo.new_arena(dt, zero=not self.all_matched)
-            self.gemm.run(A, B, Cc)
+            Cc = self.Lo.new_arena(dt, zero=(not self.all_matched) or (self.shard is not None and self._transport == "none"))
             if self.shard is not None and self.shard[1] > 1:
-                from .parallel import gather_ranges
-                gather_ranges(Cc, self.ranges, self.shard[0])
+                from . import parallel
+                if self._transport == "p2p":
+                    # own sectors -> symmetric staging arena; barrier; pull every slice into the result
+                    if self._stage is None:
+                        self._stage = parallel.symm_staging(self, Cc.numel(), dt, Cc.device)
+                    stage = self._stage
+                    self.gemm.run(A, B, stage.bufs[stage.turn])
+                    parallel.gather_p2p(stage, Cc, self.ranges, self.shard[0])
+                else:
+                    self.gemm.run(A, B, Cc)
+                    if self._transport == "nccl":
+                        parallel.gather_ranges(Cc, self.ranges, self.shard[0])
+            else:
+                self.gemm.run(A, B, Cc)
         out = UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.mem_rowrank, self.Lo, Cc)
         if self.out_rowrank != self.mem_rowrank:
             out.rowrank = self.out_rowrank
@@ -493,7 +508,7 @@ def contract_key(a, b):
 def get_contract_plan(a, b):
     from . import parallel
     shard = parallel.current_shard()
-    key = (contract_key(a, b), shard)
+    key = (contract_key(a, b), shard, parallel._STATE["transport"] if shard else None)
     pl = _CONTRACTS.get(key)
     if pl is None:
         pl = ContractPlan(a, b, shard)

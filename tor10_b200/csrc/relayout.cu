@@ -20,6 +20,7 @@
 // in registers) and walks the rows of its tile with the loads of several rows in flight.
 // Source sectors (32 B) touched by neighbouring rows of a tile are served from L1.
 #include <algorithm>
+#include <cstring>
 
 #include "t10_common.cuh"
 
@@ -358,6 +359,61 @@ extern "C" int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int
                                                          (const int2*)d_index, npairs);
   else
     T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "relayout_index: dtype %d not supported", dtype);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+// ---------------------------------------------------------------- peer gather -------
+// Sector gather over NVLink peer memory (multi-GPU Contract): every rank's finished sectors sit in its
+// own symmetric staging buffer; this kernel PULLS all the slices this rank does not own (P2P loads,
+// 16-byte vectors, all peers in flight at once) into the local output arena.  One launch, no NCCL.
+struct PeerSegs {
+  int n;
+  const void* src[16];   // peer (or local) staging base pointers
+  int64_t lo[16];        // element range [lo, hi) of the slice, same offsets in staging and arena
+  int64_t hi[16];
+  int64_t vec_start[17]; // prefix sum of slice lengths in 16-byte vectors
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather_peers(T* __restrict__ dst, const __grid_constant__ PeerSegs ps) {
+  constexpr int VE = 16 / sizeof(T);
+  const int64_t total = ps.vec_start[ps.n];
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    int sgm = 0;
+#pragma unroll 1
+    while (v >= ps.vec_start[sgm + 1]) ++sgm;
+    const int64_t e = ps.lo[sgm] + (v - ps.vec_start[sgm]) * VE;
+    const int4 val = *reinterpret_cast<const int4*>(reinterpret_cast<const T*>(ps.src[sgm]) + e);
+    *reinterpret_cast<int4*>(dst + e) = val;
+  }
+}
+
+extern "C" int t10_gather_peers(int dtype, void* d_dst, int nseg, const void* const* h_src,
+                                const int64_t* h_lo, const int64_t* h_hi, t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  T10_REQUIRE(nseg >= 0 && nseg <= 16, T10_ERR_INVALID, "gather_peers: at most 16 segments");
+  T10_REQUIRE(dtype == T10_F64 || dtype == T10_F32, T10_ERR_UNSUPPORTED, "gather_peers: dtype %d", dtype);
+  const int ve = dtype == T10_F64 ? 2 : 4;
+  PeerSegs ps;
+  memset(&ps, 0, sizeof(ps));
+  ps.n = nseg;
+  for (int i = 0; i < nseg; ++i) {
+    T10_REQUIRE(h_lo[i] % ve == 0 && h_hi[i] % ve == 0 && h_hi[i] >= h_lo[i], T10_ERR_INVALID,
+                "gather_peers: slice bounds must be multiples of 16 bytes");
+    T10_REQUIRE(((uintptr_t)h_src[i] & 15) == 0 && ((uintptr_t)d_dst & 15) == 0, T10_ERR_INVALID,
+                "gather_peers: buffers must be 16-byte aligned");
+    ps.src[i] = h_src[i];
+    ps.lo[i] = h_lo[i];
+    ps.hi[i] = h_hi[i];
+    ps.vec_start[i + 1] = ps.vec_start[i] + (h_hi[i] - h_lo[i]) / ve;
+  }
+  const int64_t total = ps.vec_start[nseg];
+  if (total == 0) return T10_OK;
+  unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  if (dtype == T10_F64) k_gather_peers<double><<<grid, 256, 0, st>>>((double*)d_dst, ps);
+  else k_gather_peers<float><<<grid, 256, 0, st>>>((float*)d_dst, ps);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }

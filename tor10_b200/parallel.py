@@ -14,14 +14,21 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-_STATE = {"group": None, "enabled": False}
+_STATE = {"group": None, "enabled": False, "transport": "auto"}
 
 
-def enable(group=None):
+def enable(group=None, transport="auto"):
+    """transport: "p2p"  = symmetric-memory staging + one pull kernel over NVLink peer memory + device barrier,
+                  "nccl" = all_gather_into_tensor through a staging buffer,
+                  "none" = results stay sharded: every rank holds only its own sectors (others are zero),
+                  "auto" = p2p on NCCL process groups when symmetric memory is available, else nccl."""
     if not dist.is_initialized():
         raise RuntimeError("tor10_b200.parallel.enable(): torch.distributed is not initialised")
+    if transport not in ("auto", "p2p", "nccl", "none"):
+        raise ValueError("transport must be auto | p2p | nccl | none")
     _STATE["group"] = group
     _STATE["enabled"] = True
+    _STATE["transport"] = transport
 
 
 def disable():
@@ -86,15 +93,105 @@ def arena_ranges(layout, bounds):
     return out
 
 
-def gather_ranges(arena, ranges, rank, group=None):
-    """In-place variable-size all-gather: after the call every rank holds all slices.  NCCL: one
-    coalesced group of broadcasts (torch's uneven all_gather); gloo (CPU tests): one broadcast per owner."""
+_STAGE = {}
+_SYMM = {}
+
+
+class _SymmStaging:
+    """Two symmetric-memory staging arenas per (device, dtype, size), used alternately so that ONE device
+    barrier per gather suffices (a rank may run one step ahead of its peers, never two)."""
+
+    def __init__(self, n, dtype, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm_mem.empty(n, dtype=dtype, device=device)
+            t.zero_()     # sectors no rank ever writes (unmatched, padding) must read as zero
+            self.hdls.append(symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD))
+            self.bufs.append(t)
+        self.turn = 0
+        self.args = {}
+        self.n = n
+        self.world = dist.get_world_size(group)
+        self.peer_ptrs = [[int(h.get_buffer(r, (n,), dtype).data_ptr()) for r in range(self.world)]
+                          for h in self.hdls]
+
+
+def symm_staging(owner, n, dtype, device, group=None):
+    """Staging arenas are private to one plan (`owner`): regions a plan never writes stay zero."""
     group = _STATE["group"] if group is None else group
-    slices = [arena[lo:hi] for lo, hi in ranges]
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather(slices, slices[rank], group=group)
-    else:
-        for r, sl in enumerate(slices):
-            if sl.numel():
-                dist.broadcast(sl, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    key = (id(owner), device.index, dtype, n)
+    st = _SYMM.get(key)
+    if st is None:
+        st = _SymmStaging(n, dtype, device, group)
+        _SYMM[key] = st
+    return st
+
+
+def transport_for(group=None):
+    group = _STATE["group"] if group is None else group
+    t = _STATE["transport"]
+    if t != "auto":
+        return t
+    if dist.get_backend(group) != "nccl":
+        return "nccl"          # (gloo tests: broadcast path inside gather_ranges)
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return "p2p"
+    except Exception:
+        return "nccl"
+
+
+def gather_p2p(stage, arena, ranges, rank):
+    """`stage` = this step's symmetric staging arena (GEMM output of every rank's own sectors).  Device
+    barrier, then one kernel pulls the peers' slices over NVLink and copies the local slice."""
+    import ctypes as C
+    from . import _lib
+    k = stage.turn
+    stage.hdls[k].barrier(channel=0)
+    args = stage.args.get(k)
+    if args is None:   # ctypes argument arrays are built once per staging buffer
+        segs = [(stage.peer_ptrs[k][r], lo, hi) for r, (lo, hi) in enumerate(ranges) if hi > lo]
+        n = len(segs)
+        args = (n, (C.c_void_p * n)(*[p for p, _, _ in segs]), (C.c_int64 * n)(*[a for _, a, _ in segs]),
+                (C.c_int64 * n)(*[b for _, _, b in segs]), _lib.dtype_code(arena.dtype))
+        stage.args[k] = args
+    n, src, lo, hi, dcode = args
+    _lib.check(_lib.load().t10_gather_peers(dcode, arena.data_ptr(), n, src, lo, hi, _lib.stream_ptr()))
+    stage.turn ^= 1
+    return arena
+
+
+def gather_ranges(arena, ranges, rank, group=None):
+    """In-place variable-size all-gather: after the call every rank holds all slices.
+    NCCL: ONE equal-size `all_gather_into_tensor` through a persistent staging buffer (every rank sends
+    max_len elements starting at its slice; the tail beyond a shorter slice is ignored), then the peers'
+    slices are copied to their place -- measured 2.5x cheaper per call than torch's uneven `all_gather`
+    (a coalesced group of broadcasts) at 25 MB.  gloo (CPU tests): one broadcast per owner."""
+    group = _STATE["group"] if group is None else group
+    world = len(ranges)
+    if dist.get_backend(group) != "nccl":
+        for r, (lo, hi) in enumerate(ranges):
+            if hi > lo:
+                dist.broadcast(arena[lo:hi], src=dist.get_global_rank(group, r) if group is not None else r,
+                               group=group)
+        return arena
+    max_len = max(hi - lo for lo, hi in ranges)
+    if max_len == 0:
+        return arena
+    lo, hi = ranges[rank]
+    key = (arena.device.index, arena.dtype, world, max_len)
+    stage = _STAGE.get(key)
+    if stage is None:
+        stage = torch.empty(world * max_len, device=arena.device, dtype=arena.dtype)
+        _STAGE[key] = stage
+    if lo + max_len <= arena.numel():
+        send = arena[lo:lo + max_len]
+    else:  # last slice is shorter than max_len and sits at the end of the arena
+        send = stage.new_empty(max_len)
+        send[:hi - lo].copy_(arena[lo:hi])
+    dist.all_gather_into_tensor(stage, send, group=group)
+    for r, (plo, phi) in enumerate(ranges):
+        if r != rank and phi > plo:
+            arena[plo:phi].copy_(stage[r * max_len:r * max_len + (phi - plo)])
     return arena
