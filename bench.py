@@ -339,14 +339,18 @@ def main():
                                           + 1)),
         "roofline": {"kernel": "k_ggemm_f64 (grouped DMMA GEMM)", "bound": "tensor", "achieved": gemm_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
-                     "traffic": None, "ms": gemm_ms, "rank_share_of_flops": share,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                     # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 50.05 MB + 3.13 MB
+                     "traffic": 53.18e6 if (world == 1 and args.chi == 4096) else None,
+                     "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
                      "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
                                     "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "
                                     "fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe)},
-        "roofline_relayout": {"kernel": "k_relayout_blocks", "bound": "hbm",
+        "roofline_relayout": {"kernel": "k_relayout_index (block relayout replayed through its element index)", "bound": "hbm",
                               "achieved": rel_bytes / (rel_ms * 1e-3) / 1e9 if rel_ms else None, "peak": hbm_peak,
                               "unit": "GB/s", "frac": rel_bytes / (rel_ms * 1e-3) / 1e9 / hbm_peak if rel_ms else None,
-                              "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src},
+                              "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src,
+                              "traffic": 37.73e6 if (world == 1 and args.chi == 4096) else None},
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:

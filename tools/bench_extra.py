@@ -181,4 +181,7 @@ if __name__ == "__main__":
         c2_dense()
     if "c1" in which:
         c1_itebd()
-        c1_itebd(chi=256, steps=40)
+        try:
+            c1_itebd(chi=64, steps=100)
+        except Exception as e:   # large chi: truncated singular values reach 0 and Inverse(lb) fails, as in the reference
+            emit(item="C1 iTEBD chi=64", failed=str(e)[:200])
