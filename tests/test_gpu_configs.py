@@ -128,3 +128,42 @@ def test_c5_peps_environment_network(T):
         assert np.array_equal(x, y)
     for k, t in prod.items():                          # labels restored (Network.py:379-380)
         assert t.labels.tolist() == specs[k]["labels"]
+
+
+def test_symmetric_svd_truncate_extension(T):
+    """Sector-wise SVD with one global truncation (the reference refuses symmetric tensors):
+    U.S.V reproduces the tensor exactly without truncation, and equals the best rank-k approximation of the
+    densified matrix with it (singular values == those of the dense matrix)."""
+    chi = 20
+    v = u1z2_leg(chi, -3, 3, 1.3)
+    p = [[1, 1], [-1, 1]]
+    spec = {"bonds": [bond(chi, -1, v), bond(2, -1, p), bond(2, 1, p), bond(chi, 1, v)], "rowrank": 2,
+            "labels": [1, 2, 4, 5]}
+    th = psym(T, spec, seed=77, device=DEV)
+    o = osym(spec, seed=77)
+    dense = o.to_dense().reshape(chi * 2, 2 * chi)
+    U, S, V = T.Svd_truncate(th)
+    back = T.Contract(T.Contract(U, S), V)
+    assert back.labels.tolist() == [1, 2, 4, 5] and back.rowrank == 2
+    assert np.array_equal(back._block_qnums, th._block_qnums)
+    for x, y in zip(blocks_np(back.Contiguous()), blocks_np(th)):
+        assert rel_err(x, y) <= 1e-12
+    s_dense = np.linalg.svd(dense, compute_uv=False)
+    s_all = np.sort(np.concatenate([np.diag(b) for b in blocks_np(S)]))[::-1]
+    nz = s_dense > 1e-12 * s_dense[0]
+    assert rel_err(s_all[:nz.sum()], s_dense[nz]) <= 1e-10
+    keep = 9
+    U, S, V = T.Svd_truncate(th, keep)
+    assert S.bonds[0].dim == keep and U.bonds[-1].dim == keep and V.bonds[0].dim == keep
+    kept = np.sort(np.concatenate([np.diag(b) for b in blocks_np(S)]))[::-1]
+    assert rel_err(kept, s_dense[:keep]) <= 1e-10
+    back = T.Contract(T.Contract(U, S), V).Contiguous()
+    ud, sd, vd = np.linalg.svd(dense)
+    best = (ud[:, :keep] * sd[:keep]) @ vd[:keep]
+    got = np.zeros_like(dense)
+    for blk, ki, bi in zip(blocks_np(back), back._Ket_invmapper_blks, back._Bra_invmapper_blks):
+        rows = ki[:, 0] * 2 + ki[:, 1]
+        cols = bi[:, 0] * chi + bi[:, 1]
+        got[np.ix_(rows, cols)] = blk
+    if sd[keep - 1] - sd[keep] > 1e-8:          # unique best approximation
+        assert rel_err(got, best) <= 1e-9

@@ -171,8 +171,86 @@ def f1_blockmap(chi=4096):
               "68.3 ms without relayout (SURVEY 6)")
 
 
+def _u1z2_leg(chi, qlo, qhi, sigma):
+    q = orc.gauss_u1_qnums(chi, qlo, qhi, sigma)[:, 0]
+    return sorted([[int(x), int(x) % 2] for x in q], reverse=True)
+
+
+def c4_u1z2(chi=2048):
+    """Config 4 hot path: two-site update of a U1xZ2 MPS -- symmetric Contract, then the sector-wise
+    Svd_truncate (torch/cuSOLVER on device, timed separately as the north star prescribes)."""
+    syms = [["U1", 0], ["Zn", 2]]
+    v = _u1z2_leg(chi, -16, 15, 5.0)
+    p = [[1, 1], [-1, 1]]
+
+    def bd(dim, bt, qn):
+        return {"dim": dim, "btype": bt, "qnums": qn, "syms": syms}
+    A = {"bonds": [bd(chi, -1, v), bd(2, -1, p), bd(chi, 1, v)], "rowrank": 2, "labels": [1, 2, 3]}
+    B = {"bonds": [bd(2, 1, p), bd(chi, -1, v), bd(chi, 1, v)], "rowrank": 2, "labels": [4, 3, 5]}
+    a, b = psym(T, A, seed=1401, device=dev), psym(T, B, seed=1402, device=dev)
+    pl = T._plan.get_contract_plan(a, b)
+    ms = timed(lambda: T.Contract(a, b), n=30)
+    th = T.Contract(a, b)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    U, S, V = T.Svd_truncate(th, chi)
+    torch.cuda.synchronize()
+    svd_s = time.perf_counter() - t0
+    emit(item="C4 U1xZ2 two-site update chi=%d" % chi, sectors=len(pl.matched), gflop=pl.flops_total / 1e9,
+         contract_ms=ms, contract_gflops=pl.flops_total / ms / 1e6, svd_truncate_s=svd_s,
+         kept=int(S.bonds[0].dim), updates_per_s_contract_only=1e3 / ms, updates_per_s_with_svd=1.0 / (svd_s + ms * 1e-3),
+         note="Svd_truncate = %d cuSOLVER SVDs (torch default driver), one per sector" % len(th.Storage))
+
+
+def c5_peps(D=8, chi=512):
+    """Config 5: absorbing one double-layer PEPS site into a boundary tensor, as a Network of U1 tensors
+    (E: chi x D x D x chi boundary tensor, P and its conjugate Pc: D^4 x d site tensors)."""
+    u1 = [["U1", 0]]
+    cq = sorted(orc.gauss_u1_qnums(chi, -6, 5, 2.0).tolist(), reverse=True)
+    dq = sorted(orc.gauss_u1_qnums(D, -1, 1, 0.8).tolist(), reverse=True)
+    pq = [[1], [-1]]
+
+    def bd(dim, bt, qn):
+        return {"dim": dim, "btype": bt, "qnums": qn, "syms": u1}
+    specs = {
+        # E[(x); (u, u', y)]
+        "E": {"bonds": [bd(chi, -1, cq), bd(D, 1, dq), bd(D, 1, dq), bd(chi, 1, cq)], "rowrank": 1, "labels": [0, 1, 2, 3]},
+        # P[(u, l); (r, d, s)]   Pc[(u', l', s); (r', d')]
+        "P": {"bonds": [bd(D, -1, dq), bd(D, -1, dq), bd(D, 1, dq), bd(D, 1, dq), bd(2, 1, pq)], "rowrank": 2,
+              "labels": [0, 1, 2, 3, 4]},
+        "Pc": {"bonds": [bd(D, -1, dq), bd(D, -1, dq), bd(2, -1, pq), bd(D, 1, dq), bd(D, 1, dq)], "rowrank": 3,
+               "labels": [0, 1, 2, 3, 4]},
+    }
+    net = ("E: 10; 11 12 13\nP: 11 20; 21 22 30\nPc: 12 23 30; 24 25\n"
+           "TOUT: 10 20 23; 13 21 22 24 25\nOrder: (E,P),Pc\n")
+    N = T.Network()
+    N.Fromstring(net)
+    ts = {k: psym(T, sp, seed=1500 + i, device=dev) for i, (k, sp) in enumerate(specs.items())}
+    for k, t in ts.items():
+        N.Put(k, t)
+    N.Launch()
+    before = dict(T._plan.STATS)
+    ms = timed(lambda: N.Launch(), n=20)
+    assert T._plan.STATS == before, "relaunch must replay cached plans"
+    plans = [pl for key, pl in T._plan._CONTRACTS.items() if isinstance(pl, T._plan.ContractPlan) and pl.Lo.rank >= 5]
+    flops = sum(pl.flops_total for pl in plans)
+    # algorithmic bytes: GEMM operands + results, plus read+write of every relayouted operand
+    nbytes = sum(8.0 * pl.gemm_bytes + sum(16.0 * r.moved_elems for r in (pl.rel_a, pl.rel_b) if r is not None)
+                 for pl in plans)
+    emit(item="C5 PEPS double-layer site absorption D=%d chi=%d" % (D, chi), ms=ms, gflop=flops / 1e9,
+         gflops=flops / ms / 1e6, algorithmic_GB=nbytes / 1e9, GBs=nbytes / ms / 1e6,
+         arithmetic_intensity=flops / nbytes, relayouts=sum((pl.rel_a is not None) + (pl.rel_b is not None) for pl in plans),
+         index_replay=[bool(r.d_index is not None) for pl in plans for r in (pl.rel_a, pl.rel_b) if r is not None],
+         note="Network.Launch of 3 U1 tensors (2 Contracts + final Permute), plans replayed; contracting over single "
+              "D=8 bonds makes this HBM-bound (K <= 64 per sector)")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["f1", "c3", "c2", "c1"]
+    which = sys.argv[1:] or ["f1", "c3", "c2", "c4", "c5", "c1"]
+    if "c4" in which:
+        c4_u1z2()
+    if "c5" in which:
+        c5_peps()
     if "f1" in which:
         f1_blockmap()
     if "c3" in which:

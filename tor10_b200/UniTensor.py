@@ -659,16 +659,10 @@ class UniTensor:
 
     # ------------------------------------------------------------------ linalg wrappers
     def Svd(self):
-        if self.is_symm:
-            raise Exception("UniTensor.Svd", "[ERROR] cannot perform Svd on a symmetry,block-form tensor. use GetBlock() "
-                                             "first and perform svd on the Block.")
         from . import linalg
         return linalg.Svd(self)
 
     def Svd_truncate(self, keepdim=None):
-        if self.is_symm:
-            raise Exception("UniTensor.Svd_truncate", "[ERROR] cannot perform Svd on a symmetry,block-form tensor. use "
-                                                      "GetBlock() first and perform svd on the Block.")
         from . import linalg
         return linalg.Svd_truncate(self, keepdim)
 

@@ -193,15 +193,70 @@ def _svd(a, keepdim, who):
     return tu, ts, tv
 
 
+def _svd_sym(a, keepdim):
+    """Sector-wise SVD of a symmetric tensor split as (row bonds | col bonds), with ONE global truncation to the
+    `keepdim` largest singular values over all sectors (EXTENSION: the reference refuses symmetric tensors,
+    linalg.py:630-631 / UniTensor.py:1672-1680).  Returns symmetric tensors
+        U [row bonds ; x]     x = new BRA bond carrying the kept sector charges
+        S [x' ; x]            block-diagonal, one diagonal block per kept sector
+        V [x' ; col bonds]    x' = the same bond as KET
+    so that Contract(Contract(U, S), V) reproduces (the truncation of) `a`.  The per-sector SVDs run on the
+    device through torch/cuSOLVER; only the kept counts come back to the host (they size the new bond)."""
+    from .Bond import BD_BRA, BD_KET
+    src = a.Contiguous()
+    L = src._layout
+    views = L.views(src._arena_tensor())
+    drv = os.environ.get("TOR10_SVD_DRIVER") if src.device.type == "cuda" else None
+    fac = [torch.linalg.svd(v, full_matrices=False, driver=drv or None) for v in views]
+    counts = [int(f[1].numel()) for f in fac]
+    total = sum(counts)
+    if keepdim is None:
+        keep = counts
+    else:
+        if keepdim <= 0 or keepdim > total:
+            raise ValueError("Svd_truncate", "[ERROR] the keepdim=%d is invalid, must larger than 0 and smaller than "
+                                             "the total number of eigenvalues." % keepdim)
+        all_s = torch.cat([f[1] for f in fac])
+        sec_id = torch.cat([torch.full((c,), i, dtype=torch.int64, device=all_s.device) for i, c in enumerate(counts)])
+        top = torch.topk(all_s, keepdim).indices
+        keep = torch.bincount(sec_id[top], minlength=len(counts)).cpu().tolist()   # prefix of every sector
+    kept = [(i, k) for i, k in enumerate(keep) if k > 0]
+    K = sum(k for _, k in kept)
+    newq = np.concatenate([np.repeat(L.block_qnums[i][None, :], k, axis=0) for i, k in kept], axis=0)
+    syms = src.bonds[0].sym_types
+    rr = src.rowrank
+    tmp = _new_label(a)
+    dev, dt = src.device, src.dtype
+    xb = Bond(K, BD_BRA, qnums=newq.tolist(), sym_types=syms)
+    xk = Bond(K, BD_KET, qnums=newq.tolist(), sym_types=syms)
+    U = UniTensor(bonds=list(src.bonds[:rr]) + [xb], rowrank=rr, labels=list(src.labels[:rr]) + [tmp - 1],
+                  device=dev, dtype=dt)
+    S = UniTensor(bonds=[xk, xb], rowrank=1, labels=[tmp - 1, tmp - 2], device=dev, dtype=dt)
+    V = UniTensor(bonds=[xk] + list(src.bonds[rr:]), rowrank=1, labels=[tmp - 2] + list(src.labels[rr:]),
+                  device=dev, dtype=dt)
+    uv, sv, vv = (t._layout.views(t._arena) for t in (U, S, V))
+    for i, k in kept:
+        q = L.block_qnums[i]
+        u, s_, vh = fac[i]
+        uv[U._layout.sector_of(q)].copy_(u[:, :k])
+        sv[S._layout.sector_of(q)].copy_(torch.diag(s_[:k]))
+        vv[V._layout.sector_of(q)].copy_(vh[:k, :])
+    return U, S, V
+
+
 def Svd(a):
     if not isinstance(a, UniTensor):
         raise Exception("Svd(UniTensor)", "[ERROR] Svd can only accept UniTensor")
+    if a.is_symm:
+        return _svd_sym(a, None)
     return _svd(a, None, "svd")
 
 
 def Svd_truncate(a, keepdim=None):
     if not isinstance(a, UniTensor):
         raise Exception("Svd_truncate(UniTensor,int)", "[ERROR] Svd_truncate can only accept UniTensor")
+    if a.is_symm:
+        return _svd_sym(a, keepdim)
     return _svd(a, keepdim, "svd")
 
 
