@@ -173,7 +173,9 @@ typedef struct t10_gemm_problem {
 /* Tile decomposition used by t10_ggemm for `tile_cfg` (FP64; all BK = 16):
  *   0: 64x64, 4 stages   1: 128x128   2: 128x64   3: 64x64, 3 stages, 3 CTAs/SM (default)
  *   40: 64x64 and 42: 64x128, aligned-only kernel (every lda/ldb/offset even, bases 16-byte aligned)
- *   100: SIMT cross-check kernel (tests).  FP32 uses the SIMT kernel with 64x64 tiles (cfg 0).
+ *   100: SIMT cross-check kernel (tests).
+ * FP32: cfg 50 (default) = tcgen05 / TMEM kernel, 128x128x32 tiles, 3xTF32 split with chunked
+ *   round-to-nearest accumulation (fp32 accuracy); cfg 0 = SIMT.
  * t10_ggemm_slots: number of co-resident CTAs of that kernel on the current device (needs CUDA).
  * t10_ggemm_plan_tiles (host only): fills h_tiles [cap,4] = {problem, m0, n0, 0}; call with
  * h_tiles = NULL to size.  With nslots > 0 the tiles are assigned to `nslots` CTA slots by LPT on a
@@ -194,6 +196,9 @@ int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d
               int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
               const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
               int32_t* d_sched, t10_stream_t stream);
+
+/* 1 through *h_flag if a tcgen05 launch ever gave up waiting on an MMA barrier (synchronises). */
+int t10_ggemm_tf32_status(int* h_flag);
 
 /* Peak-rate probes used by bench.py for the roofline denominators (register-resident loops;
  * mode 1: DMMA, 0: DFMA, 2: DMMA and DFMA warps side by side -- measured 37.0 / 36.5 / 36.8 TF on

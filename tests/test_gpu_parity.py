@@ -239,6 +239,62 @@ def test_contract_fp32(T):
         assert rel_err(blk, ref) <= TOL32
 
 
+@pytest.mark.parametrize("f32cfg", ["50", "0"])
+@pytest.mark.parametrize("chi", [40, 96, 200])
+def test_contract_fp32_kernels(T, chi, f32cfg, monkeypatch):
+    """fp32 grouped GEMM, both kernels: 50 = tcgen05 / TMEM (kind::tf32, three-pass split; the default) and
+    0 = SIMT.  Within the north star's 1e-5 of the fp64 oracle -- a single TF32 pass would sit at ~5e-4."""
+    import ctypes
+    monkeypatch.setenv("TOR10_F32_CFG", f32cfg)
+    T._plan.clear_caches()
+    A, B = _c3_spec(chi, -5, 4, 2.0)
+    a = psym(T, A, seed=15, device=DEV, dtype=torch.float32)
+    b = psym(T, B, seed=16, device=DEV, dtype=torch.float32)
+    oa, ob = osym(A, seed=15), osym(B, seed=16)
+    Cc = T.Contract(a, b)
+    if DEV == "cuda":
+        torch.cuda.synchronize()
+        flag = ctypes.c_int(0)
+        T._lib.check(T._lib.load().t10_ggemm_tf32_status(ctypes.byref(flag)))
+        assert flag.value == 0, "a tcgen05 CTA gave up waiting on its MMA barrier"
+    oc = orc.contract_sym(oa, ob)
+    assert Cc.dtype == torch.float32
+    worst = max(rel_err(blk, ref) for blk, ref in zip(blocks_np(Cc), oc.blocks))
+    assert worst <= TOL32, worst
+    # dense fp32 Matmul with ragged sizes through the same kernel
+    g = torch.Generator().manual_seed(chi)
+    x = torch.rand((chi + 3, 77), generator=g, dtype=torch.float32).to(DEV)
+    y = torch.rand((77, 2 * chi + 1), generator=g, dtype=torch.float32).to(DEV)
+    ux = T.UniTensor(bonds=[T.Bond(chi + 3), T.Bond(77)], rowrank=1, device=torch.device(DEV), dtype=torch.float32)
+    uy = T.UniTensor(bonds=[T.Bond(77), T.Bond(2 * chi + 1)], rowrank=1, device=torch.device(DEV), dtype=torch.float32)
+    ux.Storage, uy.Storage = x, y
+    got = T.Matmul(ux, uy).Storage.cpu().numpy()
+    want = x.cpu().double().numpy() @ y.cpu().double().numpy()
+    assert rel_err(got, want) <= TOL32
+    T._plan.clear_caches()
+
+
+def test_matmul_fp32_tcgen05_long_k(T):
+    """Default fp32 kernel on a long, ragged k loop (1000 = 31 slabs + 8: four accumulator chunks, the last
+    one partial) with more tiles than SMs (TMEM reused across tiles) and all-positive data, the worst case for
+    the tensor core's truncating accumulator: the chunked round-to-nearest drain must keep fp32 quality."""
+    import ctypes
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand((1601, 1000), generator=g, dtype=torch.float32).to(DEV)
+    y = torch.rand((1000, 1702), generator=g, dtype=torch.float32).to(DEV)
+    ux = T.UniTensor(bonds=[T.Bond(1601), T.Bond(1000)], rowrank=1, device=torch.device(DEV), dtype=torch.float32)
+    uy = T.UniTensor(bonds=[T.Bond(1000), T.Bond(1702)], rowrank=1, device=torch.device(DEV), dtype=torch.float32)
+    ux.Storage, uy.Storage = x, y
+    got = T.Matmul(ux, uy).Storage.cpu().numpy()
+    if DEV == "cuda":
+        flag = ctypes.c_int(0)
+        T._lib.check(T._lib.load().t10_ggemm_tf32_status(ctypes.byref(flag)))
+        assert flag.value == 0
+    want = x.cpu().double().numpy() @ y.cpu().double().numpy()
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 3e-6, err      # measured 1.9e-6; cuBLAS fp32 sits at ~4e-6 on such data
+
+
 def test_contract_plan_is_cached_and_repeatable(T):
     A, B = _c3_spec(64, -4, 3, 1.5)
     a, b = psym(T, A, seed=11, device=DEV), psym(T, B, seed=12, device=DEV)

@@ -28,6 +28,10 @@ def clear_caches():
     _LAYOUTS.clear()
     _RELAYOUTS.clear()
     _CONTRACTS.clear()
+    import sys
+    mod = sys.modules.get(__package__ + ".UniTensor")
+    if mod is not None:
+        mod._GEMM_GROUPS.clear()
 
 
 def _dev_index(device):
@@ -319,7 +323,10 @@ class GemmGroup:
         self.nprob = len(self.problems)
         self.dtype_code = _lib.dtype_code(dtype)
         if tile_cfg is None:
-            tile_cfg = pick_tile_cfg(self.problems) if dtype == torch.float64 else 0
+            if dtype == torch.float64:
+                tile_cfg = pick_tile_cfg(self.problems)
+            else:   # fp32: tcgen05 3xTF32 kernel (50, default) or the SIMT kernel (0)
+                tile_cfg = int(os.environ.get("TOR10_F32_CFG", "50"))
         self.tile_cfg = int(tile_cfg)
         pr = self.problems
         self.aligned = bool(((pr["lda"] % 2 == 0) & (pr["ldb"] % 2 == 0) & (pr["a_off"] % 2 == 0)

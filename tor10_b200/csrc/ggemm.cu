@@ -10,8 +10,8 @@
 // cp.async multi-stage pipeline global -> shared (zero-filled at ragged edges through the
 // src-size operand), conflict-free padded shared layouts, DMMA from shared fragments,
 // predicated vector stores.
-// FP32: SIMT register-tiled kernel (fp32 FMA keeps the 1e-5 bound of the north star; a
-// tcgen05 kind::tf32 3-pass split is the planned replacement).
+// FP32: tile_cfg 50 (default) = tcgen05 / TMEM kind::tf32 three-pass split, ggemm_tf32.cu;
+// tile_cfg 0 / 100 = SIMT register-tiled fp32 FMA kernel (comparison path).
 #include <algorithm>
 #include <vector>
 
@@ -641,9 +641,14 @@ static int dispatch_f64(int tile_cfg, bool launch, int* nslots_out, const double
   }
 }
 
+// ggemm_tf32.cu
+int launch_ggemm_tf32x3(const float* A, const float* B, float* C, const t10_gemm_problem* prob, int64_t ntiles,
+                        const int32_t* tiles, cudaStream_t st);
+
 static bool tile_dims(int cfg, int* bm, int* bn, int* bk) {
   *bk = 16;
   switch (cfg) {
+    case 50: *bm = 128; *bn = 128; *bk = 32; return true;
     case 0: case 3: case 40: case 100: *bm = 64; *bn = 64; return true;
     case 1: *bm = 128; *bn = 128; return true;
     case 2: *bm = 128; *bn = 64; return true;
@@ -745,8 +750,10 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
   if (dtype == T10_F64) {  // cfg 100: cross-check path used by the tests
     k_ggemm_simt<double><<<grid, 256, 0, st>>>((const double*)d_A, (const double*)d_B, (double*)d_C, d_prob,
                                                ntiles, (const int4*)d_tiles);
+  } else if (dtype == T10_F32 && tile_cfg == 50) {
+    return launch_ggemm_tf32x3((const float*)d_A, (const float*)d_B, (float*)d_C, d_prob, ntiles, d_tiles, st);
   } else if (dtype == T10_F32) {
-    T10_REQUIRE(tile_cfg == 0 || tile_cfg == 100, T10_ERR_INVALID, "fp32 ggemm uses 64x64 tiles (cfg 0)");
+    T10_REQUIRE(tile_cfg == 0 || tile_cfg == 100, T10_ERR_INVALID, "fp32 ggemm: cfg 0 (SIMT) or 50 (tcgen05)");
     k_ggemm_simt<float><<<grid, 256, 0, st>>>((const float*)d_A, (const float*)d_B, (float*)d_C, d_prob,
                                               ntiles, (const int4*)d_tiles);
   } else {
