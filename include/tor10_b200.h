@@ -187,15 +187,23 @@ int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_problem* h_
                          int64_t cap, int32_t* h_tiles, int32_t* h_slot_start, int64_t* ntiles);
 
 /* Grouped GEMM over the matched sectors: one persistent launch.  Tile schedule:
- *   d_sched != NULL      dynamic: CTAs pull tiles from the heaviest-first list (built with nslots = 0)
- *                        through d_sched[0]; d_sched is a zero-initialised int32[2] owned by the caller
- *                        and private to one stream (the kernel resets it before it exits);
- *   d_slot_start != NULL static LPT slots (grid = nslots);
- *   neither              grid-strided walk (grid = min(ntiles, resident CTAs)).            */
+ *   d_sched and d_slot_start   SM bins (fp64 kernels 0..3): the slot table built with nslots = number of
+ *                        SMs holds one LPT bin per SM; the CTAs resident on an SM pull its tiles through
+ *                        d_sched[2 + bin] and steal from other bins when theirs is empty.  d_sched is a
+ *                        zero-initialised int32[2 + nslots];
+ *   d_sched only         dynamic: CTAs pull tiles from the heaviest-first list (built with nslots = 0)
+ *                        through d_sched[0]; d_sched is a zero-initialised int32[2];
+ *   d_slot_start only    static LPT slots (grid = nslots);
+ *   neither              grid-strided walk (grid = min(ntiles, resident CTAs)).
+ * d_sched is owned by the caller and private to one stream (the kernel resets it before it exits).   */
 int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d_C,
               int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
               const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
               int32_t* d_sched, t10_stream_t stream);
+
+/* Profiling aid: while d_trace != NULL the fp64 kernels 0..3 record, per tile t of the tile table,
+ * d_trace[4t..4t+3] = {SM id, CTA, globaltimer at start, globaltimer at end} (uint64).  NULL turns it off. */
+int t10_ggemm_set_trace(void* d_trace);
 
 /* 1 through *h_flag if a tcgen05 launch ever gave up waiting on an MMA barrier (synchronises). */
 int t10_ggemm_tf32_status(int* h_flag);

@@ -70,6 +70,7 @@ SIGNATURES = {
     "t10_ggemm_plan_tiles": [_i, _l, _p, _l, _l, _p, _p, _p],
     "t10_ggemm": [_i, _i, _p, _p, _p, _l, _p, _l, _p, _l, _p, _p, _p],
     "t10_ggemm_tf32_status": [_p],
+    "t10_ggemm_set_trace": [_p],
     "t10_probe_f64_peak": [_i, _i, _p, _p],
     "t10_probe_f64_occupancy": [_i, _i, _p, _p],
 }

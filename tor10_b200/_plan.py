@@ -337,15 +337,27 @@ class GemmGroup:
         ns = C.c_int(0)
         with torch.cuda.device(device):
             check(lib.t10_ggemm_slots(self.dtype_code, self.tile_cfg, C.byref(ns)))
+        # schedule: "smbins" = one LPT bin per SM shared by the SM's resident CTAs through counters (kernels
+        # 0..3), "slots" = one static LPT slot per resident CTA, "dynamic" = one global counter
         mode = os.environ.get("TOR10_GGEMM_SCHED", "slots")
         f64k = dtype == torch.float64 and self.tile_cfg != 100
-        use_slots = f64k and (mode == "slots" or (mode == "dynamic" and self.tile_cfg in ALIGNED_CFGS))
-        self.d_sched = torch.zeros(2, dtype=torch.int32, device=device) \
-            if (f64k and mode == "dynamic" and self.tile_cfg not in ALIGNED_CFGS) else None
+        counters_ok = f64k and self.tile_cfg not in ALIGNED_CFGS
+        smbins = mode == "smbins" and counters_ok
+        use_slots = f64k and (mode == "slots" or smbins or (mode in ("dynamic", "smbins") and not counters_ok))
         nt = C.c_int64(0)
         check(lib.t10_ggemm_plan_tiles(self.tile_cfg, self.nprob, np_ptr(self.problems), 0, 0, None, None,
                                        C.byref(nt)))
-        self.nslots = min(int(ns.value), max(int(nt.value), 1)) if use_slots else 0
+        if smbins:
+            nsm = C.c_int(0)
+            z = C.c_int(0)
+            check(lib.t10_device_props(device.index if device.index is not None else torch.cuda.current_device(),
+                                       C.byref(nsm), C.byref(z), C.byref(z), C.byref(z)))
+            self.nslots = int(nsm.value)
+            self.d_sched = torch.zeros(2 + self.nslots, dtype=torch.int32, device=device)
+        else:
+            self.nslots = min(int(ns.value), max(int(nt.value), 1)) if use_slots else 0
+            self.d_sched = torch.zeros(2, dtype=torch.int32, device=device) \
+                if (mode == "dynamic" and counters_ok) else None
         tiles = np.zeros((max(nt.value, 1), 4), dtype=np.int32)
         slots = np.zeros(self.nslots + 1, dtype=np.int32)
         check(lib.t10_ggemm_plan_tiles(self.tile_cfg, self.nprob, np_ptr(self.problems), self.nslots, nt.value,

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
 k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
             double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
             int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start,
-            int32_t* __restrict__ sched) {
+            int32_t* __restrict__ sched, int nbins, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next[2];
   double* As = smem;
@@ -155,34 +155,102 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
   const int wm0 = (warp / Cfg::WARPS_N) * Cfg::WM, wn0 = (warp % Cfg::WARPS_N) * Cfg::WN;
 
   // Tile schedule, one of
+  //   sm-bins  (sched != NULL and slot_start != NULL): the slot table holds one LPT bin per SM; the CTAs
+  //            resident on an SM pull that SM's tiles (heaviest first) through sched[2 + bin], so the SM's
+  //            tensor pipe stays fed until the whole bin is done, then steal from other bins.  Balance is at
+  //            SM granularity (6 tiles per bin on the north-star workload instead of 2 per CTA slot).
+  //            Correctness never depends on which SM a CTA lands on: every tile is claimed exactly once.
   //   dynamic  (sched != NULL): CTAs pull the next tile of the heaviest-first list through an atomic
-  //            counter (list scheduling on measured, not modelled, tile times; the last CTA to leave
-  //            resets the two counters for the next launch on the stream)
+  //            counter (list scheduling on measured, not modelled, tile times)
   //   slots    (slot_start != NULL): this CTA's LPT slot, tiles[slot_start[b] .. slot_start[b+1])
   //   strided  grid-strided walk over the heaviest-first list
+  // In both counter modes the last CTA to leave resets the counters for the next launch on the stream.
+  const bool smbins = sched != nullptr && slot_start != nullptr;
   int64_t t_beg = blockIdx.x, t_end = ntiles, t_step = gridDim.x;
-  if (slot_start != nullptr) {
+  if (slot_start != nullptr && !smbins) {
     t_beg = slot_start[blockIdx.x];
     t_end = slot_start[blockIdx.x + 1];
     t_step = 1;
   }
-  if (sched != nullptr) {
+  int my_bin = 0, pending = 0;       // warp 0: this SM's bin; lane 0: the claim in flight on it
+  bool own_open = true;              // warp 0, uniform: the own bin may still hold tiles
+  if (smbins) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    my_bin = (int)(smid % (unsigned)nbins);
+  }
+  // warp 0 only: resolve the claim in flight on the own bin, or steal; returns a tile index or -1
+  auto next_smbin = [&]() -> int {
+    int t = -1;
+    if (own_open) {
+      const int idx = __shfl_sync(0xffffffffu, pending, 0);
+      if (slot_start[my_bin] + idx < slot_start[my_bin + 1]) t = slot_start[my_bin] + idx;
+      else own_open = false;
+    }
+    for (int base = 1; t < 0 && base < nbins; base += 32) {
+      const int off = base + lane;
+      int b2 = 0, left = 0;
+      if (off < nbins) {
+        b2 = (my_bin + off) % nbins;
+        left = (slot_start[b2 + 1] - slot_start[b2]) - *((volatile int32_t*)&sched[2 + b2]);
+      }
+      unsigned cand = __ballot_sync(0xffffffffu, left > 0);
+      while (t < 0 && cand) {
+        const int src = __ffs(cand) - 1;
+        int got = -1;
+        if (lane == src) {
+          const int idx = atomicAdd(&sched[2 + b2], 1);
+          if (slot_start[b2] + idx < slot_start[b2 + 1]) got = slot_start[b2] + idx;
+        }
+        t = __shfl_sync(0xffffffffu, got, src);
+        cand &= cand - 1;
+      }
+    }
+    return t;
+  };
+  if (smbins) {
+    if (warp == 0) {
+      if (lane == 0) pending = atomicAdd(&sched[2 + my_bin], 1);
+      const int t0 = next_smbin();
+      if (lane == 0) s_next[0] = t0;
+    }
+    __syncthreads();
+  } else if (sched != nullptr) {
     if (threadIdx.x == 0) s_next[0] = atomicAdd(&sched[0], 1);
     __syncthreads();
   }
   for (int64_t t = t_beg, it = 0;; t += t_step, ++it) {
-    if (sched != nullptr) {
+    if (smbins) {
+      t = s_next[it & 1];
+      if (t < 0) break;
+    } else if (sched != nullptr) {
       t = s_next[it & 1];
       if (t >= ntiles) break;
-      // claim the tile after this one now: the atomic's latency hides behind this tile's k-loop; the
-      // barrier at the end of the iteration publishes it
-      if (threadIdx.x == 0) s_next[(it + 1) & 1] = atomicAdd(&sched[0], 1);
     } else if (t >= t_end) {
       break;
     }
+    // Counter modes claim the NEXT tile a few k-steps before this one ends: late enough that the claim
+    // reflects who really finishes first (claiming at the start of a tile would hand out two tiles per CTA
+    // at t = 0, a static round-robin), early enough that the atomic's latency hides behind the last k-steps.
+    auto claim_next = [&]() {
+      if (smbins) {
+        if (warp == 0 && own_open && lane == 0) pending = atomicAdd(&sched[2 + my_bin], 1);
+      } else if (sched != nullptr) {
+        if (threadIdx.x == 0) pending = atomicAdd(&sched[0], 1);
+      }
+    };
     const int4 tile = tiles[t];
     const t10_gemm_problem p = prob[tile.x];
     const int m0 = tile.y, n0 = tile.z;
+    if (trace != nullptr && threadIdx.x == 0) {   // profiling aid (t10_ggemm_set_trace): {smid, cta, t0, t1} per tile
+      unsigned smid;
+      unsigned long long now;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[4 * t + 0] = smid;
+      trace[4 * t + 1] = blockIdx.x;
+      trace[4 * t + 2] = now;
+    }
     const double* A = Abase + p.a_off + (int64_t)m0 * p.lda;
     const double* B = Bbase + p.b_off + n0;
     const int m_rem = p.m - m0, n_rem = p.n - n0;
@@ -218,11 +286,14 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
       if (s < KT) issue_stage(s);
       cp_async_commit();
     }
+    const int claim_kt = max(KT - 4, 0);
+    if (KT == 0) claim_next();
     for (int kt = 0; kt < KT; ++kt) {
       cp_async_wait<Cfg::STAGES - 2>();
       __syncthreads();
       if (kt + Cfg::STAGES - 1 < KT) issue_stage(kt + Cfg::STAGES - 1);
       cp_async_commit();
+      if (kt == claim_kt) claim_next();
       const double* as = As + (kt % Cfg::STAGES) * Cfg::A_STAGE + (wm0 + g) * Cfg::LDA + tig;
       const double* bs = Bs + (kt % Cfg::STAGES) * Cfg::B_STAGE + tig * Cfg::LDB + wn0 + g;
       if (full) {
@@ -279,6 +350,17 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
         }
       }
     }
+    if (trace != nullptr && threadIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[4 * t + 3] = now;
+    }
+    if (smbins && warp == 0) {
+      const int tn = next_smbin();
+      if (lane == 0) s_next[(it + 1) & 1] = tn;
+    } else if (!smbins && sched != nullptr && threadIdx.x == 0) {
+      s_next[(it + 1) & 1] = pending;
+    }
     __syncthreads();  // stages free for the next tile; next tile index visible
   }
   if (sched != nullptr && threadIdx.x == 0) {
@@ -286,6 +368,7 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
     if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {
       sched[0] = 0;
       sched[1] = 0;
+      for (int b = 0; b < nbins; ++b) sched[2 + b] = 0;
       __threadfence();
     }
   }
@@ -566,6 +649,8 @@ using CfgC = F64Cfg<128, 64, 64, 32, 4>;      // tile_cfg 2: 128 thr, 116.7 KB s
 using CfgD = F64Cfg<64, 64, 32, 32, 3>;       // tile_cfg 3: 128 thr, 56.8 KB smem, 3 CTAs/SM (default)
 using CfgL = F64Cfg<64, 128, 32, 64, 3>;      // tile_cfg 42: cuBLAS's large-GEMM shape, 128 thr, 82.9 KB
 
+static unsigned long long* g_trace = nullptr;   // t10_ggemm_set_trace
+
 // launch == false: only report the number of resident CTA slots (sm_count x CTAs/SM)
 template <class Cfg, int MIN_CTAS, bool RAGGED = true>
 static int launch_f64(bool launch, int* nslots_out, const double* A, const double* B, double* C,
@@ -585,13 +670,19 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
     return T10_OK;
   }
   unsigned grid;
-  if (slot_start != nullptr) {
+  int nbins = 0;
+  if (slot_start != nullptr && sched != nullptr) {          // SM bins: every resident CTA slot, bins = nslots
+    T10_REQUIRE(nslots >= 1, T10_ERR_INVALID, "bin table without bins");
+    nbins = (int)nslots;
+    grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
+  } else if (slot_start != nullptr) {
     T10_REQUIRE(nslots >= 1, T10_ERR_INVALID, "slot table without slots");
     grid = (unsigned)nslots;
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched,
+                                                    nbins, g_trace);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -739,8 +830,8 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
                          int32_t* d_sched, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ntiles == 0 || nprob == 0) return T10_OK;
-  T10_REQUIRE(d_sched == nullptr || d_slot_start == nullptr, T10_ERR_INVALID,
-              "ggemm: dynamic schedule and slot table are mutually exclusive");
+  T10_REQUIRE(d_sched == nullptr || d_slot_start == nullptr || (dtype == T10_F64 && tile_cfg >= 0 && tile_cfg <= 3),
+              T10_ERR_INVALID, "ggemm: SM-bin schedule (counters + bin table) needs the fp64 kernels 0..3");
   T10_REQUIRE(ntiles > 0 && nprob > 0, T10_ERR_INVALID, "negative counts");
   if (dtype == T10_F64 && tile_cfg != 100)
     return dispatch_f64(tile_cfg, true, nullptr, (const double*)d_A, (const double*)d_B, (double*)d_C, d_prob,
@@ -760,6 +851,11 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
     T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "ggemm: dtype %d not supported", dtype);
   }
   T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+extern "C" int t10_ggemm_set_trace(void* d_trace) {
+  t10::g_trace = (unsigned long long*)d_trace;
   return T10_OK;
 }
 
