@@ -167,3 +167,67 @@ def test_symmetric_svd_truncate_extension(T):
         got[np.ix_(rows, cols)] = blk
     if sd[keep - 1] - sd[keep] > 1e-8:          # unique best approximation
         assert rel_err(got, best) <= 1e-9
+
+
+def _densify(t):
+    D_ = np.zeros([bdx.dim for bdx in t.bonds])
+    for blk, ki, bi in zip(blocks_np(t), t._Ket_invmapper_blks, t._Bra_invmapper_blks):
+        for i in range(blk.shape[0]):
+            for j in range(blk.shape[1]):
+                D_[tuple(ki[i]) + tuple(bi[j])] = blk[i, j]
+    return D_
+
+
+@pytest.mark.parametrize("space", ["row", "col"])
+def test_symmetric_combine_bonds(T, space):
+    """CombineBonds on a symmetric tensor = permute + relayout (family 2) + a rebuilt block map
+    (family 1) for the fused bond; the stored numbers do not move again.  Checked against the densified tensor:
+    the fused bond's index is the row-major index over the combined bonds, and its charge table is the fold of
+    their charges in that order (Bond.py:367-378)."""
+    chi = 12
+    v = u1z2_leg(chi, -2, 2, 1.1)
+    p = [[1, 1], [-1, 1]]
+    spec = {"bonds": [bond(chi, -1, v), bond(2, -1, p), bond(2, 1, p), bond(chi, 1, v)], "rowrank": 2,
+            "labels": [5, 6, 7, 8]}
+    a = psym(T, spec, seed=77, device=DEV)
+    ref = _densify(a)                                          # [a, s, t, b]
+    if space == "row":
+        a.CombineBonds([6, 5], new_label=9)                    # fused row bond (s, a): s is the slow index
+        assert a.labels.tolist() == [9, 7, 8] and a.rowrank == 1
+        want = ref.transpose(1, 0, 2, 3).reshape(2 * chi, 2, chi)
+        fused, parts = a.bonds[0], (T.Bond(2, T.BD_KET, qnums=p, sym_types=[T.Symmetry.U1(), T.Symmetry.Zn(2)]),
+                                    T.Bond(chi, T.BD_KET, qnums=v, sym_types=[T.Symmetry.U1(), T.Symmetry.Zn(2)]))
+    else:
+        a.CombineBonds([8, 7])                                 # fused column bond (b, t)
+        assert a.labels.tolist() == [5, 6, 8] and a.rowrank == 2
+        want = ref.transpose(0, 1, 3, 2).reshape(chi, 2, 2 * chi)
+        fused, parts = a.bonds[2], (T.Bond(chi, T.BD_BRA, qnums=v, sym_types=[T.Symmetry.U1(), T.Symmetry.Zn(2)]),
+                                    T.Bond(2, T.BD_BRA, qnums=p, sym_types=[T.Symmetry.U1(), T.Symmetry.Zn(2)]))
+    assert a.is_contiguous() and len(a.bonds) == 3
+    assert np.array_equal(_densify(a), want)
+    expect = parts[0]
+    expect.combine(parts[1])
+    assert fused.dim == 2 * chi and np.array_equal(fused.qnums, expect.qnums)
+    # mixed tags are refused like in the reference (UniTensor.py:4018-4021)
+    b = psym(T, spec, seed=78, device=DEV)
+    with pytest.raises(Exception):
+        b.CombineBonds([6, 7])
+
+
+def test_symmetric_matmul_chain(T):
+    """Matmul / Chain_matmul of symmetric rank-2 tensors = sector-wise product on the grouped GEMM."""
+    chi = 40
+    v = u1z2_leg(chi, -3, 3, 1.3)
+    w = u1z2_leg(28, -2, 3, 1.2)
+    A = {"bonds": [bond(chi, -1, v), bond(28, 1, w)], "rowrank": 1, "labels": [0, 1]}
+    B = {"bonds": [bond(28, -1, w), bond(chi, 1, v)], "rowrank": 1, "labels": [0, 1]}
+    a, b = psym(T, A, seed=5, device=DEV), psym(T, B, seed=6, device=DEV)
+    c = T.Matmul(a, b)
+    assert c.labels.tolist() == [0, 1] and c.rowrank == 1 and a.labels.tolist() == [0, 1]
+    da, db = _densify(a), _densify(b)
+    assert rel_err(_densify(c), da @ db) <= 1e-12
+    d = T.Chain_matmul(a, b, a)
+    assert rel_err(_densify(d), da @ db @ da) <= 1e-12
+    dense = T.UniTensor(bonds=[T.Bond(chi), T.Bond(28)], rowrank=1, device=torch.device(DEV))
+    with pytest.raises(Exception):
+        T.Matmul(a, dense)

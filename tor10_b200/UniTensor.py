@@ -1191,16 +1191,66 @@ def Contract(a, b):
     return _dense_result(a, b, tmp, list(range(len(a.labels))), list(range(len(b.labels))))
 
 
+def _combine_bonds_sym(a, idxs, idx_no_combine, permute_back):
+    """Symmetric branch of _CombineBonds (UniTensor.py:4012-4093).
+
+    As in the reference the combined bonds must share one bra/ket tag and become the WHOLE row space
+    (when idxs[0] is a row bond) or the WHOLE column space: the tensor is permuted so that the combined
+    bonds are adjacent, relaid out (family-2 kernel), and the fused bond replaces them.  The flat row
+    (column) index of the fused bond is exactly the flat index the block map already uses, so the arena is
+    untouched and only the block map is rebuilt (family-1 kernel) for the new bond list.
+
+    Deviations from the reference, both forced by reference defects:
+      * its row branch always raises (`np.arange(..., dype=...)`, UniTensor.py:4053);
+      * its column branch lays the bonds out in REVERSED order (`idxs[::-1]`, :4060) but fuses the charges
+        in forward order (:4075-4079), so the fused bond's charge table does not describe the stored
+        columns; here both use the order given in `idxs` (first = slowest index), and the debug prints
+        (:4064, :4082) are dropped."""
+    if len(np.unique(a.braket[idxs])) != 1:
+        raise Exception("_CombineBonds", "[ERROR], label_to_combine should be all bra-bond or all ket-bond for "
+                                         "Tensor with symmetry")
+    n, nc = len(a.labels), len(idxs)
+    if idxs[0] < a.rowrank:
+        a.Permute(np.concatenate((idxs, idx_no_combine)), rowrank=nc, by_label=False)
+        a.Contiguous_()
+        nb = copy.copy(a.bonds[0])
+        nb.combine(list(a.bonds[1:nc]))
+        bonds = [nb] + list(a.bonds[nc:])
+        labels = np.concatenate((a.labels[:1], a.labels[nc:]))
+        braket = np.concatenate((a.braket[:1], a.braket[nc:]))
+        rowrank = 1
+    else:
+        k = n - nc
+        a.Permute(np.concatenate((idx_no_combine, idxs)), rowrank=k, by_label=False)
+        a.Contiguous_()
+        nb = copy.copy(a.bonds[k])
+        nb.combine(list(a.bonds[k + 1:]))
+        bonds = list(a.bonds[:k]) + [nb]
+        labels, braket = a.labels[:k + 1].copy(), a.braket[:k + 1].copy()
+        rowrank = k
+    arena = a._arena_tensor()
+    old = a._layout
+    new = _plan.get_layout(bonds, braket, rowrank, arena.device)
+    if not (np.array_equal(new.block_qnums, old.block_qnums) and np.array_equal(new.rows, old.rows)
+            and np.array_equal(new.cols, old.cols) and np.array_equal(new.arena_off, old.arena_off)):
+        raise RuntimeError("_CombineBonds: internal error, fused block map differs from the unfused one")
+    a.bonds = np.array(bonds, dtype=object)
+    a.labels, a.braket, a.rowrank = np.array(labels, dtype=np.int64), np.array(braket, dtype=np.int64), rowrank
+    a._layout, a._blocks, a._block_qnums = new, None, None
+    a._set_mapper(np.arange(len(bonds), dtype=np.int64))
+    a._check_braket()
+    if permute_back:
+        a.braket_form()
+
+
 def _CombineBonds(a, idxs, new_label, permute_back):
-    """UniTensor.py:3967-4207, dense tensors.  (Symmetric CombineBonds is a 'next' row of SURVEY 8f.)"""
+    """UniTensor.py:3967-4207."""
     if not isinstance(a, UniTensor):
         raise Exception("_CombineBonds(UniTensor,int_arr)", "[ERROR] )CombineBonds can only accept UniTensor")
     if a.is_diag:
         raise TypeError("_CombineBonds", "[ERROR] CombineBonds doesn't support diagonal matrix.")
     if len(idxs) == 1:
         return
-    if a.is_symm:
-        raise NotImplementedError("tor10_b200: CombineBonds on symmetric tensors is not built yet (SURVEY 8f-4)")
     idx_no_combine = np.setdiff1d(np.arange(len(a.labels)), idxs)
     old_shape = np.array(a.shape)
     combined_dim = int(np.prod(old_shape[idxs]))
@@ -1210,6 +1260,8 @@ def _CombineBonds(a, idxs, new_label, permute_back):
             raise Exception("_CombineBonds", "[ERROR], cannot set new_label to %d as there will be duplicate bond with "
                                              "this label after combined" % newlbl)
         a.labels[idxs[0]] = newlbl
+    if a.is_symm:
+        return _combine_bonds_sym(a, np.asarray(idxs, dtype=np.int64), idx_no_combine, permute_back)
     new_bond = copy.copy(a.bonds[idxs[0]])
     new_bond.combine(list(a.bonds[idxs[1:]]))
     if a.braket is not None and not all(a.braket[i] == a.braket[idxs[0]] for i in idxs):

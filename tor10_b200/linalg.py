@@ -260,14 +260,32 @@ def Svd_truncate(a, keepdim=None):
     return _svd(a, keepdim, "svd")
 
 
+def _matmul_sym(a, b):
+    """Matmul of two symmetric rank-2 tensors (extension; the reference aborts, linalg.py:699-700):
+    the sector-wise product on the grouped-GEMM kernel, i.e. Contract over a's column bond and b's row bond.
+    Operands are not modified; the result carries the default labels [0, 1] like the dense Matmul."""
+    import copy
+    from .UniTensor import Contract
+    if not (a.is_symm and b.is_symm):
+        raise Exception("Matmul(a,b)", "[ERROR] cannot multiply a symmetric with a non-symmetric UniTensor")
+    if not (len(a.labels) == 2 and len(b.labels) == 2 and a.rowrank == 1 and b.rowrank == 1):
+        raise Exception("Matmul(a,b)", "Matmul can only accept two UniTensor with each has 1 inbond and 1 outbond")
+    ta, tb = copy.copy(a), copy.copy(b)
+    ta.labels = np.array([-1, -2], dtype=np.int64)
+    tb.labels = np.array([-2, -3], dtype=np.int64)
+    out = Contract(ta, tb)
+    out.labels = np.array([0, 1], dtype=np.int64)
+    return out
+
+
 def Matmul(a, b):
     """linalg.py:680-737.  diag x diag: the reference returns the DOT PRODUCT of the two diagonals flagged
     is_diag (torch.matmul of two 1-D tensors, :717-722) -- a bug; the element-wise product (the diagonal
-    of the matrix product) is returned here instead."""
+    of the matrix product) is returned here instead.  Symmetric operands: see _matmul_sym."""
     if not (isinstance(a, UniTensor) and isinstance(b, UniTensor)):
         raise TypeError("_Matmul(a,b)", "[ERROR] _Matmul can only accept UniTensors for both a & b")
     if a.is_symm or b.is_symm:
-        raise Exception("Matmul(a,b)", "[Abort] Matmul cannot operate on sym TN.")
+        return _matmul_sym(a, b)
     if a.braket is not None or b.braket is not None:
         raise Exception("Matmul(a,b)", "Matmul can only accept two regular Tensors")
     if not (len(a.labels) == 2 and len(b.labels) == 2 and a.rowrank == 1 and b.rowrank == 1):
@@ -294,13 +312,13 @@ def Chain_matmul(*args):
     if not all(isinstance(x, UniTensor) for x in args):
         raise TypeError("_Chain_matmul(*args)", "[ERROR] _Chain_matmul can only accept UniTensors for all elements in "
                                                 "args")
-    if any(x.is_symm for x in args):
-        raise Exception("Chain_matmul(*args)", "[Abort] Chain multiplication for symm tensor(s) are under developing.")
     if not all(len(x.labels) == 2 and x.rowrank == 1 for x in args):
         raise Exception("Chain_matmul(*args)", "Chain mult should have all UniTensor have 1 inbond 1 outbond")
     out = args[0]
     for nxt in args[1:]:
         out = Matmul(out, nxt)
+    if out.is_symm:      # extension (the reference aborts, linalg.py:764-765): chain of sector-wise products
+        return out
     res = UniTensor(bonds=[args[0].bonds[0], args[-1].bonds[1]], rowrank=1, check=False)
     res._mac(torch_tensor=torch.diag(out._dense) if out.is_diag else out._dense)
     return res
