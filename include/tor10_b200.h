@@ -201,6 +201,23 @@ int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d
               const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
               int32_t* d_sched, t10_stream_t stream);
 
+/* Fused grouped GEMM -> all-gather (fp64, kernels 0..3; multi-GPU sector sharding, no reference counterpart:
+ * the reference is single-device).  Same as t10_ggemm, but every output tile is stored into ALL `npeers`
+ * arenas h_peer_C[0..npeers) -- this rank's staging arena and the peers', mapped through NVLink peer memory
+ * (torch symmetric memory) -- at the same element offsets, tile by tile, so the transfer overlaps the
+ * remaining tiles' math.  With h_peer_flag != NULL the last CTA to finish raises *h_peer_flag[q] (this
+ * rank's uint64 slot in rank q's flag array, peer-mapped) to `step` with system-scope release semantics;
+ * d_done_ctr is a zero-initialised int32 owned by the caller (reset by the kernel).
+ * t10_wait_copy is the consumer: it waits until d_flags[0..nflags) >= step, then copies n elements
+ * d_src -> d_dst (staging arena -> result arena).  *d_err is set if a flag does not arrive in ~2 s.      */
+int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
+                        void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
+                        int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
+                        const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
+                        int32_t* d_sched, t10_stream_t stream);
+int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t n, const void* d_flags, int nflags,
+                  uint64_t step, int32_t* d_err, t10_stream_t stream);
+
 /* Profiling aid: while d_trace != NULL the fp64 kernels 0..3 record, per tile t of the tile table,
  * d_trace[4t..4t+3] = {SM id, CTA, globaltimer at start, globaltimer at end} (uint64).  NULL turns it off. */
 int t10_ggemm_set_trace(void* d_trace);

@@ -31,13 +31,23 @@ def _worker(rank, world, port, q):
     A, B = _c3_spec(160, -7, 6, 2.5)
     a, b = psym(T, A, seed=41, device="cuda:%d" % rank), psym(T, B, seed=42, device="cuda:%d" % rank)
     single = T.Contract(a, b)
-    parallel.enable()
-    sharded = T.Contract(a, b)
-    parallel.disable()
-    torch.cuda.synchronize()
+    a32 = psym(T, A, seed=41, device="cuda:%d" % rank, dtype=torch.float32)
+    b32 = psym(T, B, seed=42, device="cuda:%d" % rank, dtype=torch.float32)
+    single32 = T.Contract(a32, b32)
     oc = orc.contract_sym(osym(A, seed=41), osym(B, seed=42))
-    same = all(torch.equal(x, y) for x, y in zip(single.Storage, sharded.Storage))
-    err = max(rel_err(x.cpu().numpy(), y) for x, y in zip(sharded.Storage, oc.blocks))
+    same, err = True, 0.0
+    # every transport, three calls each (the staging arenas are double-buffered); "auto" = fused GEMM+all-gather
+    for transport in ("auto", "fused", "p2p", "nccl"):
+        parallel.enable(transport=transport)
+        for _ in range(3):
+            sharded = T.Contract(a, b)
+            same = same and all(torch.equal(x, y) for x, y in zip(single.Storage, sharded.Storage))
+            err = max(err, max(rel_err(x.cpu().numpy(), y) for x, y in zip(sharded.Storage, oc.blocks)))
+        sh32 = T.Contract(a32, b32)      # fp32 plans cannot fuse: pull path
+        same = same and all(torch.equal(x, y) for x, y in zip(single32.Storage, sh32.Storage))
+        parallel.disable()
+        T._plan.clear_caches()
+    torch.cuda.synchronize()
     q.put((rank, same, err))
     dist.destroy_process_group()
 

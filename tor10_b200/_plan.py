@@ -10,6 +10,7 @@ The reference recomputes all of this with numpy on every call (3 block-map build
 an O(nsec^2) sector search per Contract).
 """
 import ctypes as C
+import itertools
 import os
 
 import numpy as np
@@ -300,31 +301,46 @@ def label_match(la, lb):
     return same, a_ind.astype(np.int64), b_ind.astype(np.int64), a_free.astype(np.int64), b_free.astype(np.int64)
 
 
-def pick_tile_cfg(problems):
+def pick_tile_cfg(problems, sharded=False):
     """Tile configuration of the FP64 grouped GEMM (see t10_ggemm_plan_tiles).  Measured on B200 at C3a
     (42 ragged sectors, chi=4096): 64x64x16 tiles, 3 stages, 3 CTAs/SM with fragment-granular skipping of
-    ragged edges and static LPT slots is the fastest of the twelve variants in csrc/ggemm.cu (profiles/)."""
+    ragged edges and static LPT slots is the fastest of the variants in csrc/ggemm.cu (profiles/).
+    A rank of a sector-sharded contraction that is left with fewer 64x64 tiles than 1.5 per SM switches to
+    32x32 tiles (cfg 8): with under one tile per SM the launch lasts as long as its largest tile on a lone
+    CTA (C3a on 8 GPUs: 53.5 us -> 39.6 us)."""
     forced = os.environ.get("TOR10_GGEMM_CFG")
     if forced is not None:
         return int(forced)
+    if sharded and problems is not None and len(problems):
+        m, n = problems["m"].astype(np.int64), problems["n"].astype(np.int64)
+        if int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count():
+            return 8
     return 3
 
 
+def _sm_count():
+    nsm, z = C.c_int(0), C.c_int(0)
+    check(_lib.load().t10_device_props(torch.cuda.current_device(), C.byref(nsm), C.byref(z), C.byref(z), C.byref(z)))
+    return int(nsm.value)
+
+
 ALIGNED_CFGS = (40, 42)   # kernels that require 16-byte aligned operand rows
+FUSABLE_CFGS = (0, 1, 2, 3, 8)   # kernels with the fused all-gather epilogue and the counter schedules
 FALLBACK_CFG = 3
 
 
 class GemmGroup:
     """Problem table + tile table on the device."""
 
-    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True):
+    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True, sharded=False):
         lib = _lib.load()
         self.problems = np.ascontiguousarray(problems, dtype=_lib.GEMM_PROBLEM_DTYPE)
         self.nprob = len(self.problems)
         self.dtype_code = _lib.dtype_code(dtype)
         if tile_cfg is None:
             if dtype == torch.float64:
-                tile_cfg = pick_tile_cfg(self.problems)
+                with torch.cuda.device(device):
+                    tile_cfg = pick_tile_cfg(self.problems, sharded=sharded)
             else:   # fp32: tcgen05 3xTF32 kernel (50, default) or the SIMT kernel (0)
                 tile_cfg = int(os.environ.get("TOR10_F32_CFG", "50"))
         self.tile_cfg = int(tile_cfg)
@@ -371,6 +387,21 @@ class GemmGroup:
         self.bytes = float(sum(int(p["m"]) * int(p["k"]) + int(p["k"]) * int(p["n"]) + int(p["m"]) * int(p["n"])
                                for p in self.problems))
 
+    def fusable(self):
+        """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
+        return self.dtype_code == _lib.dtype_code(torch.float64) and self.tile_cfg in FUSABLE_CFGS
+
+    def run_allgather(self, A, B, peer_ptrs, flag_ptrs, step, done_ctr):
+        """peer_ptrs / flag_ptrs: ctypes (c_void_p * n) of every rank's arena base / of this rank's flag slot
+        on every rank (this rank's own included)."""
+        check(_lib.load().t10_ggemm_allgather(self.tile_cfg, A.data_ptr(), B.data_ptr(), len(peer_ptrs), peer_ptrs,
+                                              flag_ptrs, step, done_ctr.data_ptr(),
+                                              self.nprob, self.d_prob.data_ptr(), self.ntiles,
+                                              self.d_tiles.data_ptr(), self.nslots,
+                                              self.d_slots.data_ptr() if self.nslots else None,
+                                              self.d_sched.data_ptr() if self.d_sched is not None else None,
+                                              _lib.stream_ptr()))
+
     def run(self, A, B, Cc):
         check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
                                     self.nprob, self.d_prob.data_ptr(), self.ntiles, self.d_tiles.data_ptr(),
@@ -379,10 +410,14 @@ class GemmGroup:
                                     _lib.stream_ptr()))
 
 
+_PLAN_SERIAL = itertools.count()
+
+
 class ContractPlan:
     """Symmetric Contract(a, b): UniTensor.py:3692-3743."""
 
     def __init__(self, a, b, shard=None):
+        self.serial = next(_PLAN_SERIAL)     # identity of the plan's private staging arenas (never reused)
         from .Bond import BondType, BD_KET
         STATS["contract_build"] += 1
         self.shard = shard
@@ -449,7 +484,7 @@ class ContractPlan:
         if shard is not None:
             # independent sectors are partitioned over the ranks: contiguous runs of output
             # sectors with balanced flops, so that every rank's result is ONE slice of the arena
-            from .parallel import partition_contiguous, arena_ranges
+            from .parallel import partition_contiguous, partition_lpt, arena_ranges
             rank, world = shard
             cost = np.zeros(Lo.nsec)
             for ob, ab, bb in matched:
@@ -457,7 +492,15 @@ class ContractPlan:
             bounds = partition_contiguous(cost, world)
             self.sector_bounds = bounds
             self.ranges = arena_ranges(Lo, bounds)
-            matched = [m for m in matched if bounds[rank] <= m[0] < bounds[rank + 1]]
+            owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(Lo.nsec), side="right")
+            if self._transport == "none" or (self._transport == "fused" and a.dtype == torch.float64
+                                             and pick_tile_cfg(None) in FUSABLE_CFGS):
+                # the fused GEMM -> all-gather stores tiles, not arena slices (and sharded results are not gathered
+                # at all): ownership need not be contiguous, so the sectors are balanced by LPT (the contiguous
+                # split of C3a at 2 ranks is 44 / 56 %)
+                owner = partition_lpt(cost, world)
+            self.sector_owner = owner
+            matched = [m for m in matched if owner[m[0]] == rank]
         self.matched = matched
         sec_a = sorted(set(m[1] for m in matched))
         sec_b = sorted(set(m[2] for m in matched))
@@ -478,7 +521,7 @@ class ContractPlan:
         for i, (ob, ab, bb) in enumerate(matched):
             prob[i] = (pa.off[ab], pb.off[bb], Lo.arena_off[ob], La.rows[ab], Lb.cols[bb], La.cols[ab],
                        pa.ld[ab], pb.ld[bb], Lo.cols[ob])
-        self.gemm = GemmGroup(prob, dev, a.dtype)
+        self.gemm = GemmGroup(prob, dev, a.dtype, sharded=shard is not None and shard[1] > 1)
         self.flops = self.gemm.flops
         self.gemm_bytes = self.gemm.bytes
 
@@ -494,13 +537,20 @@ class ContractPlan:
                 A = self.rel_a.run(A, torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt))
             if self.rel_b is not None:
                 B = self.rel_b.run(B, torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt))
-            Cc = self.Lo.new_arena(dt, zero=(not self.all_matched) or (self.shard is not None and self._transport == "none"))
-            if self.shard is not None and self.shard[1] > 1:
+            sharded = self.shard is not None and self.shard[1] > 1
+            fused = sharded and self._transport == "fused" and self.gemm.fusable()
+            need_zero = (not self.all_matched) or (self.shard is not None and self._transport == "none")
+            Cc = self.Lo.new_arena(dt, zero=need_zero and not fused)   # fused: overwritten by the copy-out
+            if sharded:
                 from . import parallel
-                if self._transport == "p2p":
+                if self._transport in ("fused", "p2p") and self._stage is None:
+                    self._stage = parallel.symm_staging(self, Cc.numel(), dt, Cc.device)
+                if fused:
+                    # ONE kernel: every output tile is stored into every rank's symmetric staging arena through
+                    # NVLink peer memory while the remaining tiles are computed; barrier; local copy out
+                    parallel.gemm_allgather(self._stage, self.gemm, A, B, Cc)
+                elif self._transport in ("fused", "p2p"):
                     # own sectors -> symmetric staging arena; barrier; pull every slice into the result
-                    if self._stage is None:
-                        self._stage = parallel.symm_staging(self, Cc.numel(), dt, Cc.device)
                     stage = self._stage
                     self.gemm.run(A, B, stage.bufs[stage.turn])
                     parallel.gather_p2p(stage, Cc, self.ranges, self.shard[0])

@@ -13,6 +13,7 @@
 // FP32: tile_cfg 50 (default) = tcgen05 / TMEM kind::tf32 three-pass split, ggemm_tf32.cu;
 // tile_cfg 0 / 100 = SIMT register-tiled fp32 FMA kernel (comparison path).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "t10_common.cuh"
@@ -140,12 +141,28 @@ struct LeanLoader {
   }
 };
 
+// Fused GEMM -> all-gather: when n > 0 every output tile is written to ALL of these arenas (this rank's and
+// its peers', mapped through NVLink peer memory) instead of Cbase, tile by tile, so the transfer rides under
+// the remaining tiles' math.  The tile is staged through shared memory so that each store instruction of a
+// warp covers one full 512-byte row segment (large NVLink write packets).
+// When the last CTA of the launch has stored its tiles it raises this rank's flag in every peer's flag
+// array to `step` (system-scope release); the consumer (t10_wait_copy on each rank) acquires all flags.
+constexpr int T10_MAX_PEERS = 8;
+struct PeerOut {
+  int n;
+  double* ptr[T10_MAX_PEERS];
+  unsigned long long* flag[T10_MAX_PEERS];   // this rank's slot in rank q's flag array (NULL: no signalling)
+  unsigned long long step;
+  int* done_ctr;                             // zero-initialised arrival counter of this launch (reset on exit)
+};
+
 template <class Cfg, int MIN_CTAS, bool RAGGED>
 __global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
 k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
             double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
             int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start,
-            int32_t* __restrict__ sched, int nbins, unsigned long long* __restrict__ trace) {
+            int32_t* __restrict__ sched, int nbins, unsigned long long* __restrict__ trace,
+            const __grid_constant__ PeerOut peers) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next[2];
   double* As = smem;
@@ -332,21 +349,51 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
     cp_async_wait<0>();
 
     // epilogue: lane holds C[row g][cols 2*tig, 2*tig+1] of every 8x8 fragment
-    double* C = Cbase + p.c_off;
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
+    if (peers.n > 0) {
+      // fused all-gather: registers -> shared tile -> row-contiguous 16-byte stores into every rank's arena
+      constexpr int CLD = Cfg::BN + 2;
+      static_assert(Cfg::BM * CLD <= Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE), "C tile must fit the stage memory");
+      __syncthreads();   // every warp is done reading the last stage
+      double* Cs = smem;
 #pragma unroll
-    for (int i = 0; i < Cfg::MI; ++i) {
-      const int r = m0 + wm0 + i * 8 + g;
-      if (r >= p.m) continue;
+      for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
-      for (int j = 0; j < Cfg::NI; ++j) {
-        const int c = n0 + wn0 + j * 8 + 2 * tig;
-        double* o = C + (int64_t)r * p.ldc + c;
-        if (c + 1 < p.n) {
-          if (c16) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
-          else { o[0] = acc[i][j][0]; o[1] = acc[i][j][1]; }
-        } else if (c < p.n) {
-          o[0] = acc[i][j][0];
+        for (int j = 0; j < Cfg::NI; ++j)
+          *reinterpret_cast<double2*>(Cs + (wm0 + i * 8 + g) * CLD + wn0 + j * 8 + 2 * tig) =
+              make_double2(acc[i][j][0], acc[i][j][1]);
+      __syncthreads();
+      bool p16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0);
+      for (int q = 0; q < peers.n; ++q) p16 = p16 && (((uintptr_t)peers.ptr[q] & 15) == 0);
+      for (int idx = threadIdx.x; idx < Cfg::BM * (Cfg::BN / 2); idx += Cfg::THREADS) {
+        const int r = idx / (Cfg::BN / 2), c = (idx % (Cfg::BN / 2)) * 2;
+        if (m0 + r >= p.m || n0 + c >= p.n) continue;
+        const double2 v = *reinterpret_cast<const double2*>(Cs + r * CLD + c);
+        const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
+        const bool two = n0 + c + 1 < p.n;
+#pragma unroll 1
+        for (int q = 0; q < peers.n; ++q) {
+          double* o = peers.ptr[q] + off;
+          if (two && p16) *reinterpret_cast<double2*>(o) = v;
+          else { o[0] = v.x; if (two) o[1] = v.y; }
+        }
+      }
+    } else {
+      double* C = Cbase + p.c_off;
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i) {
+        const int r = m0 + wm0 + i * 8 + g;
+        if (r >= p.m) continue;
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; ++j) {
+          const int c = n0 + wn0 + j * 8 + 2 * tig;
+          double* o = C + (int64_t)r * p.ldc + c;
+          if (c + 1 < p.n) {
+            if (c16) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else { o[0] = acc[i][j][0]; o[1] = acc[i][j][1]; }
+          } else if (c < p.n) {
+            o[0] = acc[i][j][0];
+          }
         }
       }
     }
@@ -362,6 +409,17 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
       s_next[(it + 1) & 1] = pending;
     }
     __syncthreads();  // stages free for the next tile; next tile index visible
+  }
+  if (peers.n > 0 && peers.done_ctr != nullptr && threadIdx.x == 0) {
+    // every thread's tile stores are ordered before this point by the CTA barrier that ends each tile
+    __threadfence_system();
+    if (atomicAdd(peers.done_ctr, 1) == (int)gridDim.x - 1) {
+      *peers.done_ctr = 0;
+      __threadfence_system();
+      for (int q = 0; q < peers.n; ++q)
+        if (peers.flag[q] != nullptr)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[q]), "l"(peers.step) : "memory");
+    }
   }
   if (sched != nullptr && threadIdx.x == 0) {
     __threadfence();
@@ -647,6 +705,7 @@ using CfgA = F64Cfg<64, 64, 32, 32, 4>;       // tile_cfg 0 / 40: 128 thr, 75.8 
 using CfgB = F64Cfg<128, 128, 64, 32, 4>;     // tile_cfg 1: 256 thr, 149.5 KB smem
 using CfgC = F64Cfg<128, 64, 64, 32, 4>;      // tile_cfg 2: 128 thr, 116.7 KB smem
 using CfgD = F64Cfg<64, 64, 32, 32, 3>;       // tile_cfg 3: 128 thr, 56.8 KB smem, 3 CTAs/SM (default)
+using CfgS = F64Cfg<32, 32, 16, 16, 3>;       // tile_cfg 8: 32x32 tiles, 4 warps: fine-grained units for sharded runs
 using CfgL = F64Cfg<64, 128, 32, 64, 3>;      // tile_cfg 42: cuBLAS's large-GEMM shape, 128 thr, 82.9 KB
 
 static unsigned long long* g_trace = nullptr;   // t10_ggemm_set_trace
@@ -655,7 +714,7 @@ static unsigned long long* g_trace = nullptr;   // t10_ggemm_set_trace
 template <class Cfg, int MIN_CTAS, bool RAGGED = true>
 static int launch_f64(bool launch, int* nslots_out, const double* A, const double* B, double* C,
                       const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
-                      const int32_t* slot_start, int32_t* sched, cudaStream_t st) {
+                      const int32_t* slot_start, int32_t* sched, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64<Cfg, MIN_CTAS, RAGGED>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
@@ -682,7 +741,7 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched,
-                                                    nbins, g_trace);
+                                                    nbins, g_trace, peers);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -720,12 +779,15 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
 
 static int dispatch_f64(int tile_cfg, bool launch, int* nslots_out, const double* A, const double* B, double* C,
                         const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
-                        const int32_t* slot_start, int32_t* sched, cudaStream_t st) {
+                        const int32_t* slot_start, int32_t* sched, cudaStream_t st,
+                        const PeerOut& peers = PeerOut{}) {
+  if (peers.n > 0) T10_REQUIRE((tile_cfg >= 0 && tile_cfg <= 3) || tile_cfg == 8, T10_ERR_INVALID, "fused all-gather needs fp64 kernels 0..3 or 8");
   switch (tile_cfg) {
-    case 0: return launch_f64<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 1: return launch_f64<CfgB, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 2: return launch_f64<CfgC, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 3: return launch_f64<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 0: return launch_f64<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
+    case 1: return launch_f64<CfgB, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
+    case 2: return launch_f64<CfgC, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
+    case 3: return launch_f64<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
+    case 8: return launch_f64<CfgS, 4>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     case 40: return launch_f64_v5<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
     case 42: return launch_f64_v5<CfgL, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
     default: T10_REQUIRE(false, T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
@@ -741,6 +803,7 @@ static bool tile_dims(int cfg, int* bm, int* bn, int* bk) {
   switch (cfg) {
     case 50: *bm = 128; *bn = 128; *bk = 32; return true;
     case 0: case 3: case 40: case 100: *bm = 64; *bn = 64; return true;
+    case 8: *bm = 32; *bn = 32; return true;
     case 1: *bm = 128; *bn = 128; return true;
     case 2: *bm = 128; *bn = 64; return true;
     case 42: *bm = 64; *bn = 128; return true;
@@ -830,7 +893,7 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
                          int32_t* d_sched, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ntiles == 0 || nprob == 0) return T10_OK;
-  T10_REQUIRE(d_sched == nullptr || d_slot_start == nullptr || (dtype == T10_F64 && tile_cfg >= 0 && tile_cfg <= 3),
+  T10_REQUIRE(d_sched == nullptr || d_slot_start == nullptr || (dtype == T10_F64 && ((tile_cfg >= 0 && tile_cfg <= 3) || tile_cfg == 8)),
               T10_ERR_INVALID, "ggemm: SM-bin schedule (counters + bin table) needs the fp64 kernels 0..3");
   T10_REQUIRE(ntiles > 0 && nprob > 0, T10_ERR_INVALID, "negative counts");
   if (dtype == T10_F64 && tile_cfg != 100)
@@ -852,6 +915,39 @@ extern "C" int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d
   }
   T10_LAUNCH_CHECK();
   return T10_OK;
+}
+
+__global__ void k_raise_flags(PeerOut peers) {   // a rank without tiles still has to signal
+  if (threadIdx.x < peers.n && peers.flag[threadIdx.x] != nullptr)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[threadIdx.x]), "l"(peers.step) : "memory");
+}
+
+extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers,
+                                   void* const* h_peer_C, void* const* h_peer_flag, uint64_t step,
+                                   int32_t* d_done_ctr, int64_t nprob, const t10_gemm_problem* d_prob,
+                                   int64_t ntiles, const int32_t* d_tiles, int64_t nslots,
+                                   const int32_t* d_slot_start, int32_t* d_sched, t10_stream_t stream) {
+  T10_REQUIRE(npeers >= 1 && npeers <= T10_MAX_PEERS, T10_ERR_INVALID, "ggemm_allgather: 1..%d arenas", T10_MAX_PEERS);
+  T10_REQUIRE(ntiles >= 0 && nprob >= 0, T10_ERR_INVALID, "negative counts");
+  T10_REQUIRE(h_peer_flag == nullptr || d_done_ctr != nullptr, T10_ERR_INVALID, "flags need an arrival counter");
+  PeerOut po;
+  memset(&po, 0, sizeof(po));
+  po.n = npeers;
+  po.step = step;
+  po.done_ctr = d_done_ctr;
+  for (int i = 0; i < npeers; ++i) {
+    po.ptr[i] = (double*)h_peer_C[i];
+    po.flag[i] = h_peer_flag ? (unsigned long long*)h_peer_flag[i] : nullptr;
+  }
+  if (ntiles == 0 || nprob == 0) {
+    if (h_peer_flag) {
+      k_raise_flags<<<1, 32, 0, (cudaStream_t)stream>>>(po);
+      T10_LAUNCH_CHECK();
+    }
+    return T10_OK;
+  }
+  return dispatch_f64(tile_cfg, true, nullptr, (const double*)d_A, (const double*)d_B, (double*)h_peer_C[0], d_prob,
+                      ntiles, d_tiles, nslots, d_slot_start, d_sched, (cudaStream_t)stream, po);
 }
 
 extern "C" int t10_ggemm_set_trace(void* d_trace) {

@@ -390,6 +390,51 @@ k_gather_peers(T* __restrict__ dst, const __grid_constant__ PeerSegs ps) {
   }
 }
 
+// Consumer side of the fused GEMM -> all-gather: wait until every rank's flag reached `step` (the ranks'
+// GEMM kernels raise them after their last tile store, t10_ggemm_allgather), then copy the completed staging
+// arena into the result arena.  The spin is bounded (about two seconds): on expiry *err is set and the copy
+// proceeds, so a dead peer cannot hang the device.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_wait_copy(T* __restrict__ dst, const T* __restrict__ src, int64_t nvec, const unsigned long long* flags, int nflags,
+            unsigned long long step, int* __restrict__ err) {
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < nflags; ++r) {
+      unsigned long long v = 0;
+      for (long long spin = 0; spin < 20000000ll; ++spin) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+        if (v >= step) break;
+        __nanosleep(100);
+      }
+      if (v < step) atomicExch(err, 1);
+    }
+  }
+  __syncthreads();
+  const int4* s4 = reinterpret_cast<const int4*>(src);
+  int4* d4 = reinterpret_cast<int4*>(dst);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x)
+    d4[v] = s4[v];
+}
+
+extern "C" int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t n, const void* d_flags, int nflags,
+                             uint64_t step, int32_t* d_err, t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  T10_REQUIRE(dtype == T10_F64 || dtype == T10_F32, T10_ERR_UNSUPPORTED, "wait_copy: dtype %d", dtype);
+  const int ve = dtype == T10_F64 ? 2 : 4;
+  T10_REQUIRE(n >= 0 && n % ve == 0 && nflags >= 0 && nflags <= 64, T10_ERR_INVALID, "wait_copy: bad sizes");
+  T10_REQUIRE(((uintptr_t)d_dst & 15) == 0 && ((uintptr_t)d_src & 15) == 0, T10_ERR_INVALID, "wait_copy: alignment");
+  const int64_t nvec = n / ve;
+  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nvec, 256 * 4), (int64_t)sm_count() * 4));
+  if (dtype == T10_F64)
+    k_wait_copy<double><<<grid, 256, 0, st>>>((double*)d_dst, (const double*)d_src, nvec,
+                                               (const unsigned long long*)d_flags, nflags, step, d_err);
+  else
+    k_wait_copy<float><<<grid, 256, 0, st>>>((float*)d_dst, (const float*)d_src, nvec,
+                                              (const unsigned long long*)d_flags, nflags, step, d_err);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
 extern "C" int t10_gather_peers(int dtype, void* d_dst, int nseg, const void* const* h_src,
                                 const int64_t* h_lo, const int64_t* h_hi, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;

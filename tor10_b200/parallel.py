@@ -18,14 +18,17 @@ _STATE = {"group": None, "enabled": False, "transport": "auto"}
 
 
 def enable(group=None, transport="auto"):
-    """transport: "p2p"  = symmetric-memory staging + one pull kernel over NVLink peer memory + device barrier,
-                  "nccl" = all_gather_into_tensor through a staging buffer,
-                  "none" = results stay sharded: every rank holds only its own sectors (others are zero),
-                  "auto" = p2p on NCCL process groups when symmetric memory is available, else nccl."""
+    """transport: "fused" = the grouped GEMM stores every output tile into all ranks' symmetric staging arenas
+                           (NVLink peer stores in its epilogue, overlapped with the math) + one device barrier
+                           + a local copy out; plans whose kernel cannot fuse (fp32) take the p2p path,
+                  "p2p"   = symmetric-memory staging + device barrier + one pull kernel over NVLink peer memory,
+                  "nccl"  = all_gather_into_tensor through a staging buffer,
+                  "none"  = results stay sharded: every rank holds only its own sectors (others are zero),
+                  "auto"  = fused on NCCL process groups when symmetric memory is available, else nccl."""
     if not dist.is_initialized():
         raise RuntimeError("tor10_b200.parallel.enable(): torch.distributed is not initialised")
-    if transport not in ("auto", "p2p", "nccl", "none"):
-        raise ValueError("transport must be auto | p2p | nccl | none")
+    if transport not in ("auto", "fused", "p2p", "nccl", "none"):
+        raise ValueError("transport must be auto | fused | p2p | nccl | none")
     _STATE["group"] = group
     _STATE["enabled"] = True
     _STATE["transport"] = transport
@@ -79,6 +82,19 @@ def partition_contiguous(cost, parts):
     return [int(b) for b in bounds]
 
 
+def partition_lpt(cost, parts):
+    """Owner of every item by longest-processing-time-first: heaviest item to the least loaded part.  Used
+    when ownership need not be contiguous (fused GEMM -> all-gather stores tiles, not arena slices)."""
+    cost = np.asarray(cost, dtype=np.float64)
+    owner = np.zeros(len(cost), dtype=np.int64)
+    load = np.zeros(parts)
+    for i in np.argsort(-cost, kind="stable"):
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += cost[i]
+    return owner
+
+
 def arena_ranges(layout, bounds):
     """Arena element range [lo, hi) that holds sectors bounds[r]..bounds[r+1]-1, for every rank r."""
     out = []
@@ -98,29 +114,44 @@ _SYMM = {}
 
 
 class _SymmStaging:
-    """Two symmetric-memory staging arenas per (device, dtype, size), used alternately so that ONE device
-    barrier per gather suffices (a rank may run one step ahead of its peers, never two)."""
+    """Two symmetric-memory staging arenas per plan, used alternately (a rank may run one step ahead of its
+    peers, never two), plus -- for the fused GEMM -> all-gather -- one symmetric uint64 flag array per arena
+    (slot r = "rank r has stored all its tiles of step s") and a local arrival counter."""
 
     def __init__(self, n, dtype, device, group):
         import torch.distributed._symmetric_memory as symm_mem
-        self.bufs, self.hdls = [], []
+        grp = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.bufs, self.hdls, self.flags, self.flag_hdls = [], [], [], []
         for _ in range(2):
             t = symm_mem.empty(n, dtype=dtype, device=device)
             t.zero_()     # sectors no rank ever writes (unmatched, padding) must read as zero
-            self.hdls.append(symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD))
+            f = symm_mem.empty(self.world, dtype=torch.int64, device=device)
+            f.zero_()
+            torch.cuda.synchronize(device)      # zeroed before any peer can reach them
+            self.hdls.append(symm_mem.rendezvous(t, group=grp))
+            self.flag_hdls.append(symm_mem.rendezvous(f, group=grp))
             self.bufs.append(t)
+            self.flags.append(f)
         self.turn = 0
         self.args = {}
         self.n = n
-        self.world = dist.get_world_size(group)
+        self.steps = [0, 0]
+        self.done_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.peer_ptrs = [[int(h.get_buffer(r, (n,), dtype).data_ptr()) for r in range(self.world)]
                           for h in self.hdls]
+        # address of THIS rank's slot inside rank r's flag array
+        self.peer_flag_ptrs = [[int(h.get_buffer(r, (self.world,), torch.int64).data_ptr()) + 8 * self.rank
+                                for r in range(self.world)] for h in self.flag_hdls]
+        dist.barrier(group=group)
 
 
 def symm_staging(owner, n, dtype, device, group=None):
     """Staging arenas are private to one plan (`owner`): regions a plan never writes stay zero."""
     group = _STATE["group"] if group is None else group
-    key = (id(owner), device.index, dtype, n)
+    key = (getattr(owner, "serial", id(owner)), device.index, dtype, n)
     st = _SYMM.get(key)
     if st is None:
         st = _SymmStaging(n, dtype, device, group)
@@ -137,9 +168,37 @@ def transport_for(group=None):
         return "nccl"          # (gloo tests: broadcast path inside gather_ranges)
     try:
         import torch.distributed._symmetric_memory  # noqa: F401
-        return "p2p"
+        return "fused"         # GEMM with the all-gather in its epilogue; plans that cannot fuse pull (p2p)
     except Exception:
         return "nccl"
+
+
+def gemm_allgather(stage, gemm, A, B, arena):
+    """Fused path, two launches: (1) the grouped GEMM stores every output tile into all ranks' staging arenas
+    (NVLink peer stores overlapped with the math) and its last CTA raises this rank's flag on every peer
+    (t10_ggemm_allgather); (2) t10_wait_copy acquires all ranks' flags and copies the completed staging arena
+    into the result arena (a local HBM copy).  No host-side or NCCL synchronisation on the data path."""
+    import ctypes as C
+    from . import _lib
+    k = stage.turn
+    args = stage.args.get(("push", k))
+    if args is None:
+        args = ((C.c_void_p * stage.world)(*stage.peer_ptrs[k]), (C.c_void_p * stage.world)(*stage.peer_flag_ptrs[k]))
+        stage.args[("push", k)] = args
+    stage.steps[k] += 1
+    step = stage.steps[k]
+    gemm.run_allgather(A, B, args[0], args[1], step, stage.done_ctr)
+    n = arena.numel() // 4 * 4      # whole 16-byte vectors (the arena ends in >= 16 elements of padding)
+    _lib.check(_lib.load().t10_wait_copy(_lib.dtype_code(arena.dtype), arena.data_ptr(), stage.bufs[k].data_ptr(),
+                                         n, stage.flags[k].data_ptr(), stage.world, step,
+                                         stage.err.data_ptr(), _lib.stream_ptr()))
+    stage.turn ^= 1
+    return arena
+
+
+def fused_status(stage):
+    """True if a t10_wait_copy of this staging set ever timed out waiting for a peer (synchronises)."""
+    return bool(stage.err.item())
 
 
 def gather_p2p(stage, arena, ranges, rank):
@@ -151,7 +210,10 @@ def gather_p2p(stage, arena, ranges, rank):
     stage.hdls[k].barrier(channel=0)
     args = stage.args.get(k)
     if args is None:   # ctypes argument arrays are built once per staging buffer
-        segs = [(stage.peer_ptrs[k][r], lo, hi) for r, (lo, hi) in enumerate(ranges) if hi > lo]
+        # start with the next rank's slice and wrap around: the ranks then read from different peers at any
+        # moment instead of all pulling rank 0's slice first
+        order = [(rank + 1 + i) % len(ranges) for i in range(len(ranges))]
+        segs = [(stage.peer_ptrs[k][r], ranges[r][0], ranges[r][1]) for r in order if ranges[r][1] > ranges[r][0]]
         n = len(segs)
         args = (n, (C.c_void_p * n)(*[p for p, _, _ in segs]), (C.c_int64 * n)(*[a for _, a, _ in segs]),
                 (C.c_int64 * n)(*[b for _, _, b in segs]), _lib.dtype_code(arena.dtype))
