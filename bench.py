@@ -263,11 +263,48 @@ def main():
     hB = B_arena.cpu().pin_memory()
     hC = torch.empty(plan.Lo.arena_elems + 16, dtype=dt).pin_memory()
 
+    def merged(ranges):
+        out = []
+        for lo, hi in sorted(ranges):
+            if out and lo <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], hi)
+            else:
+                out.append([lo, hi])
+        return [(int(lo), int(hi)) for lo, hi in out]
+
+    def source_ranges(rel, layout, direct_sectors):
+        """Arena ranges of the operand this rank's share of the contraction reads."""
+        if rel is None:
+            secs = direct_sectors
+        elif rel.d_index is None:
+            return [(0, int(layout.arena_elems))]
+        else:
+            idx = rel.d_index.cpu().numpy()
+            idx = idx[idx >= 0]
+            secs = np.unique(np.searchsorted(layout.arena_off, idx, side="right") - 1)
+        return merged([(layout.arena_off[s_], layout.arena_off[s_] + layout.rows[s_] * layout.cols[s_]) for s_ in secs])
+
+    if world > 1:
+        # every rank moves only what its sectors need: the source sectors its relayouts read, and its own output
+        # sectors (the union over the ranks is each operand / the result exactly once per step)
+        in_a = source_ranges(plan.rel_a, a._layout, sorted(set(m[1] for m in plan.matched)))
+        in_b = source_ranges(plan.rel_b, b._layout, sorted(set(m[2] for m in plan.matched)))
+        out_c = merged([(plan.Lo.arena_off[m[0]], plan.Lo.arena_off[m[0]] + plan.Lo.rows[m[0]] * plan.Lo.cols[m[0]])
+                        for m in plan.matched])
+    else:
+        in_a, in_b = [(0, hA.numel())], [(0, hB.numel())]
+        out_c = [(0, hC.numel())]
+    h2d_bytes = 8 * (sum(hi - lo for lo, hi in in_a) + sum(hi - lo for lo, hi in in_b))
+    d2h_bytes = 8 * sum(hi - lo for lo, hi in out_c)
+
     def e2e_step():
-        a._arena.copy_(hA, non_blocking=True)
-        b._arena.copy_(hB, non_blocking=True)
+        for lo, hi in in_a:
+            a._arena[lo:hi].copy_(hA[lo:hi], non_blocking=True)
+        for lo, hi in in_b:
+            b._arena[lo:hi].copy_(hB[lo:hi], non_blocking=True)
         c = T.Contract(a, b)
-        hC.copy_(c._arena, non_blocking=True)
+        for lo, hi in out_c:
+            hC[lo:hi].copy_(c._arena[lo:hi], non_blocking=True)
 
     for _ in range(3):
         e2e_step()
@@ -279,6 +316,19 @@ def main():
         tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
+    # ---- the same contraction in fp32 (tcgen05 / TMEM 3xTF32 grouped GEMM), informational, 1 GPU only ----
+    fp32_info = None
+    if world == 1:
+        a32 = psym(T, A, seed=1003, device=dev, dtype=torch.float32)
+        b32 = psym(T, B, seed=1004, device=dev, dtype=torch.float32)
+        for _ in range(3):
+            T.Contract(a32, b32)
+        t32 = float(np.mean(timed_loop(lambda: T.Contract(a32, b32), max(10, min(args.steps, 50)))))
+        p32 = _plan.get_contract_plan(a32, b32)
+        fp32_info = {"ms_per_step": t32, "gflops": flops / (t32 * 1e-3) / 1e9, "tile_cfg": p32.gemm.tile_cfg,
+                     "kernel": "k_ggemm_tf32x3 (tcgen05.mma kind::tf32, 3-pass split, TMEM accumulators)"
+                     if p32.gemm.tile_cfg == 50 else "k_ggemm_simt<float>"}
+        del a32, b32
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -326,17 +376,24 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "sectors": int(plan.Lo.nsec), "algorithmic_gflop": flops / 1e9,
                    "nnz_per_operand": int(a._layout.nnz), "tile_cfg": plan.gemm.tile_cfg,
-                   "parallelism": ("sectors sharded over %d GPUs (contiguous runs balanced by flops); result gathered "
-                                   "on every rank: %s" % (world, {"p2p": "symmetric-memory staging + device barrier + one "
-                                   "pull kernel over NVLink peer memory", "nccl": "NCCL all_gather_into_tensor"}.get(
-                                       parallel.transport_for(), parallel.transport_for()))) if world > 1 else "1 GPU",
+                   "parallelism": ("sectors sharded over %d GPUs (%s); result gathered on every rank: %s" % (
+                       world, "LPT by flops" if plan._transport in ("fused", "none") else "contiguous runs balanced by flops",
+                       {"fused": "all-gather fused into the GEMM epilogue (every output tile stored into all ranks' "
+                                 "symmetric staging arenas over NVLink peer memory, system-scope flags, one wait+copy "
+                                 "kernel)",
+                        "p2p": "symmetric-memory staging + device barrier + one pull kernel over NVLink peer memory",
+                        "nccl": "NCCL all_gather_into_tensor"}.get(plan._transport, str(plan._transport))))
+                   if world > 1 else "1 GPU",
                    "value_if_result_stays_sharded_gflops": (flops / (sharded_ms * 1e-3) / 1e9) if sharded_ms else None,
                    "l2": "flushed between steps (256 MiB write); every step timed by its own CUDA event pair",
                    "plan": "cached (block maps, relayout tables, tile table built once outside the timed region)"},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int((hA.numel() + hB.numel()) * 8), "d2h_bytes_per_step": int(hC.numel() * 8)},
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "note": ("bytes are this rank's (rank 0): every rank uploads the operand sectors its share reads and "
+                         "downloads its own output sectors" if world > 1 else "whole operands in, whole result out")},
+        "fp32_contract": fp32_info,
         "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
-                                          + 1)),
+                                          + 1 + ((1 if plan._transport in ("fused", "p2p") else 0) if world > 1 else 0))),
         "roofline": {"kernel": "k_ggemm_f64 (grouped DMMA GEMM)", "bound": "tensor", "achieved": gemm_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
