@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+RELAYOUT_TRAFFIC = {"index": 37.73e6, "runs": None}   # filled from the ncu captures under profiles/
 METRIC = "U1 block-sparse Contract GFLOP/s (fp64) at chi=4096"
 UNIT = "GFLOP/s"
 
@@ -276,6 +277,13 @@ def main():
         """Arena ranges of the operand this rank's share of the contraction reads."""
         if rel is None:
             secs = direct_sectors
+        elif rel.d_runs is not None:
+            rr = rel.d_runs.cpu().numpy().astype(np.int64)
+            ln = np.diff(rr[:, 0])
+            ok = rr[:-1, 1] >= 0
+            first, last = rr[:-1, 1][ok], rr[:-1, 1][ok] + ln[ok] - 1
+            secs = np.unique(np.concatenate([np.searchsorted(layout.arena_off, first, side="right") - 1,
+                                             np.searchsorted(layout.arena_off, last, side="right") - 1]))
         elif rel.d_index is None:
             return [(0, int(layout.arena_elems))]
         else:
@@ -459,11 +467,18 @@ def main():
                      "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
                                     "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "
                                     "fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe)},
-        "roofline_relayout": {"kernel": "k_relayout_index (block relayout replayed through its element index)", "bound": "hbm",
+        "roofline_relayout": {"kernel": ("k_relayout_runs (block relayout replayed through the runs of its element index)"
+                                         if (plan.rel_a is not None and plan.rel_a.d_runs is not None) else
+                                         "k_relayout_index (block relayout replayed through its element index)"
+                                         if (plan.rel_a is not None and plan.rel_a.d_index is not None) else
+                                         "k_relayout_blocks (factored tables)"), "bound": "hbm",
                               "achieved": rel_bytes / (rel_ms * 1e-3) / 1e9 if rel_ms else None, "peak": hbm_peak,
                               "unit": "GB/s", "frac": rel_bytes / (rel_ms * 1e-3) / 1e9 / hbm_peak if rel_ms else None,
                               "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src,
-                              "traffic": 37.73e6 if (world == 1 and args.chi == 4096) else None},
+                              # dram read+write of one launch, ncu --set full at chi=4096 on 1 GPU
+                              # (profiles/r01_ncu_summary.md); the destination partly stays in L2
+                              "traffic": RELAYOUT_TRAFFIC.get("runs" if (plan.rel_a is not None and plan.rel_a.d_runs is not None)
+                                                              else "index") if (world == 1 and args.chi == 4096) else None},
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -142,6 +142,14 @@ int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, int64_t ntile
 int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_index,
                        t10_stream_t stream);
 
+/* Replay of a relayout through RUNS of its element index (maximal pieces with index[i+1] == index[i]+1, or
+ * constant -1 / -2).  d_runs: int32 pairs {dst_start, src_start} sorted by dst_start, nruns real entries
+ * followed by the sentinel {n, 0}; d_chunk_first[c] = run containing destination element 1024*c, for
+ * c = 0 .. ceil(n/1024) (the last entry = nruns-1).  Same result as t10_relayout_index, without the 4 B per
+ * element of index traffic; built by the host from the emitted index (plan time).  d_dst 16-byte aligned. */
+int t10_relayout_runs(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_runs,
+                      int64_t nruns, const int32_t* d_chunk_first, t10_stream_t stream);
+
 /* Multi-GPU sector gather over NVLink peer memory (no reference counterpart: the reference has no
  * multi-device code).  dst[lo_i .. hi_i) = src_i[lo_i .. hi_i) for nseg <= 16 slices, where src_i are
  * peer-mapped (symmetric-memory) staging buffers of the other ranks; bounds multiples of 16 bytes.

@@ -189,6 +189,33 @@ def test_relayout_vs_oracle_medium(T):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("mode", ["runs", "index", "blocks"])
+def test_relayout_replay_modes(T, mode, monkeypatch):
+    """The three replays of one relayout -- runs of the element index (default when runs are long), the
+    element index, the factored block kernel -- move exactly the same bits (oracle: vectorised restatement
+    of UniTensor.py:2108-2129).  Narrow charge range = long runs (degeneracies of 40-80)."""
+    monkeypatch.setenv("TOR10_RELAYOUT_RUNS", "1" if mode == "runs" else "auto")
+    monkeypatch.setenv("TOR10_RELAYOUT_INDEX", "0" if mode == "blocks" else "1")
+    T._plan.clear_caches()
+    A, B = _c3_spec(256, -2, 2, 1.2)
+    t, o = psym(T, A, seed=31, device=DEV), osym(A, seed=31)
+    t.Permute([0, 2, 1, 3], rowrank=2)
+    o.permute([0, 2, 1, 3], rowrank=2).contiguous_(vectorised=True)
+    P = t.Contiguous()
+    for b, blk in enumerate(blocks_np(P)):
+        assert np.array_equal(blk, o.blocks[b])
+    # the same relayout inside Contract (padded operand scratch, sector subset = all)
+    a, b = psym(T, A, seed=31, device=DEV), psym(T, B, seed=32, device=DEV)
+    Cc = T.Contract(a, b)
+    pl = T._plan.get_contract_plan(a, b)
+    assert (pl.rel_a.d_runs is not None) == (mode == "runs")
+    assert (pl.rel_a.d_index is not None) == (mode == "index")
+    oc = orc.contract_sym(osym(A, seed=31), osym(B, seed=32))
+    for blk, ref in zip(blocks_np(Cc), oc.blocks):
+        assert rel_err(blk, ref) <= TOL64
+    T._plan.clear_caches()
+
+
 # ---- family 3 + Contract --------------------------------------------------------------
 def test_contract_sym_goldens(T, golden):
     z, specs = golden("contract_sym")

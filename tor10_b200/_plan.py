@@ -243,9 +243,13 @@ class RelayoutPlan:
         self.d_tiles = torch.from_numpy(tiles.view(np.uint8)).to(dev) if self.ntiles else \
             torch.zeros(32, dtype=torch.uint8, device=dev)
         self.d_index = None
+        self.d_runs = None
         self.index_n = 0
-        self.use_index = (os.environ.get("TOR10_RELAYOUT_INDEX", "1") == "1"
-                          and 4 * packed.size <= self.INDEX_BUDGET_BYTES)
+        # replay form: element index (fastest: 16.4 us cold / 8.4 us L2-warm on the C3a operand), runs of the
+        # index (18.4 / 12.4 us, ~1 % of the index's memory: taken when the index exceeds its budget, or with
+        # TOR10_RELAYOUT_RUNS=1), factored tables (24.6 / 16.6 us, no plan memory; TOR10_RELAYOUT_INDEX=0)
+        self.use_index = os.environ.get("TOR10_RELAYOUT_INDEX", "1") == "1"
+        self.index_fits = 4 * packed.size <= self.INDEX_BUDGET_BYTES
         self.moved_elems = int(sum(int(L.rows[s]) * int(L.cols[s])
                                    for s in (range(L.nsec) if sectors is None else sectors)))
 
@@ -261,12 +265,53 @@ class RelayoutPlan:
             self.CR.data_ptr(), self.CC.data_ptr(), self.M.d_rowbase.data_ptr(), self.M.d_coloff.data_ptr(),
             self.M.d_ket_map.data_ptr() if self.check else None, self.M.d_bra_map.data_ptr() if self.check else None,
             self.d_index.data_ptr(), _lib.stream_ptr()))
+        self._build_runs()
+
+    RUN_CHUNK = 1024      # RR_CHUNK of relayout.cu
+
+    def _build_runs(self):
+        """Run-length form of the element index (plan time, torch ops on the device): maximal pieces with
+        index[i+1] == index[i] + 1 (or constant -1 / -2).  Used when runs average >= 16 elements; the element
+        index is then dropped."""
+        self.d_runs = None
+        want = os.environ.get("TOR10_RELAYOUT_RUNS", "auto")
+        if want == "0" or (want == "auto" and self.index_fits):
+            if not self.index_fits:
+                self.d_index, self.use_index = None, False     # over budget and no runs: factored tables
+            return
+        n = self.index_n
+        idx = self.d_index.to(torch.int64)
+        pos = torch.arange(n, device=idx.device, dtype=torch.int64)
+        key = torch.where(idx >= 0, idx - pos, idx - (1 << 40))
+        brk = torch.ones(n, dtype=torch.bool, device=idx.device)
+        brk[1:] = key[1:] != key[:-1]
+        starts = torch.nonzero(brk).flatten()
+        nruns = int(starts.numel())
+        if nruns * 16 > n:
+            if not self.index_fits:
+                self.d_index, self.use_index = None, False
+            return
+        runs = torch.empty((nruns + 1, 2), dtype=torch.int32, device=idx.device)
+        runs[:nruns, 0] = starts.to(torch.int32)
+        runs[:nruns, 1] = idx[starts].to(torch.int32)
+        runs[nruns, 0], runs[nruns, 1] = n, 0
+        nchunks = (n + self.RUN_CHUNK - 1) // self.RUN_CHUNK
+        first = torch.clamp(torch.arange(nchunks + 1, device=idx.device, dtype=torch.int64) * self.RUN_CHUNK, max=n - 1)
+        self.d_chunk_first = (torch.searchsorted(starts, first, right=True) - 1).to(torch.int32)
+        self.d_runs, self.nruns = runs.contiguous(), nruns
+        self.d_index = None                    # 4 B per element of plan memory given back
+        self.use_index = False
 
     def run(self, src_arena, dst):
         """dst must hold packed.size elements; padding/unmatched space is left untouched."""
         if self.use_index and self.d_index is None and self.ntiles and src_arena.numel() < 2 ** 31:
             with torch.cuda.device(self.L.device):
                 self._build_index()
+        if self.d_runs is not None and dst.numel() >= self.index_n and dst.data_ptr() % 16 == 0:
+            check(_lib.load().t10_relayout_runs(_lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(),
+                                                self.index_n, self.d_runs.data_ptr(), self.nruns,
+                                                self.d_chunk_first.data_ptr(), _lib.stream_ptr()))
+            return dst
         if self.d_index is not None and dst.numel() >= self.index_n and dst.data_ptr() % 16 == 0:
             check(_lib.load().t10_relayout_index(_lib.dtype_code(src_arena.dtype), src_arena.data_ptr(),
                                                  dst.data_ptr(), self.index_n, self.d_index.data_ptr(),
