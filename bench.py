@@ -461,8 +461,8 @@ def main():
         "roofline": {"kernel": "k_ggemm_f64 (grouped DMMA GEMM)", "bound": "tensor", "achieved": gemm_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                     # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 50.05 MB + 3.13 MB
-                     "traffic": 53.18e6 if (world == 1 and args.chi == 4096) else None,
+                     # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 50.00 MB + 3.02 MB
+                     "traffic": 53.02e6 if (world == 1 and args.chi == 4096) else None,
                      "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
                      "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
                                     "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "
