@@ -346,21 +346,35 @@ def label_match(la, lb):
     return same, a_ind.astype(np.int64), b_ind.astype(np.int64), a_free.astype(np.int64), b_free.astype(np.int64)
 
 
-def pick_tile_cfg(problems, sharded=False):
-    """Tile configuration of the FP64 grouped GEMM (see t10_ggemm_plan_tiles).  Measured on B200 at C3a
-    (42 ragged sectors, chi=4096): 64x64x16 tiles, 3 stages, 3 CTAs/SM with fragment-granular skipping of
-    ragged edges and static LPT slots is the fastest of the variants in csrc/ggemm.cu (profiles/).
-    A rank of a sector-sharded contraction that is left with fewer 64x64 tiles than 1.5 per SM switches to
-    32x32 tiles (cfg 8): with under one tile per SM the launch lasts as long as its largest tile on a lone
-    CTA (C3a on 8 GPUs: 53.5 us -> 39.6 us)."""
+def pick_tile_cfg(problems, sharded=False, base_aligned=False):
+    """Tile configuration of the FP64 grouped GEMM (see t10_ggemm_plan_tiles), from measurements on B200
+    (profiles/r01_lone_cta.jsonl, r01_bench_*.json):
+      3   64x64x16, 3 stages, 3 CTAs/SM, any alignment (8-byte cp.async on odd leading dimensions), ragged
+          fragments skipped, static LPT slots -- the general kernel (C3a: 129.8 us);
+      40  same tile on the software-pipelined aligned-only kernel, 2 CTAs/SM: 33 TF against 30.6 TF in steady
+          state, C3a GEMM stage 123.9 us -- taken when every operand row is 16-byte aligned AS STORED (an
+          extra copy of an operand just to align it costs more than it gains);
+      42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned groups of at least four waves of
+          such tiles (large dense GEMMs);
+      8   32x32 tiles for a rank of a sector-sharded contraction left with fewer than 1.5 64x64 tiles per SM
+          (C3a on 8 GPUs: 53.5 us -> 39.6 us); sharded groups otherwise stay on 3 (fused all-gather epilogue)."""
     forced = os.environ.get("TOR10_GGEMM_CFG")
     if forced is not None:
         return int(forced)
-    if sharded and problems is not None and len(problems):
-        m, n = problems["m"].astype(np.int64), problems["n"].astype(np.int64)
+    if problems is None or not len(problems):
+        return 3
+    m, n = problems["m"].astype(np.int64), problems["n"].astype(np.int64)
+    if sharded:
         if int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count():
             return 8
-    return 3
+        return 3
+    aligned = base_aligned and bool(((problems["lda"] % 2 == 0) & (problems["ldb"] % 2 == 0)
+                                     & (problems["a_off"] % 2 == 0) & (problems["b_off"] % 2 == 0)).all())
+    if not aligned:
+        return 3
+    if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
+        return 42
+    return 40
 
 
 def _sm_count():
@@ -385,7 +399,7 @@ class GemmGroup:
         if tile_cfg is None:
             if dtype == torch.float64:
                 with torch.cuda.device(device):
-                    tile_cfg = pick_tile_cfg(self.problems, sharded=sharded)
+                    tile_cfg = pick_tile_cfg(self.problems, sharded=sharded, base_aligned=bool(base_aligned))
             else:   # fp32: tcgen05 3xTF32 kernel (50, default) or the SIMT kernel (0)
                 tile_cfg = int(os.environ.get("TOR10_F32_CFG", "50"))
         self.tile_cfg = int(tile_cfg)
