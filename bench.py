@@ -290,14 +290,14 @@ def main():
             idx = rel.d_index.cpu().numpy()
             idx = idx[idx >= 0]
             secs = np.unique(np.searchsorted(layout.arena_off, idx, side="right") - 1)
-        return merged([(layout.arena_off[s_], layout.arena_off[s_] + layout.rows[s_] * layout.cols[s_]) for s_ in secs])
+        return merged([(layout.arena_off[s_], layout.arena_off[s_] + layout.rows[s_] * layout.ld[s_]) for s_ in secs])
 
     if world > 1:
         # every rank moves only what its sectors need: the source sectors its relayouts read, and its own output
         # sectors (the union over the ranks is each operand / the result exactly once per step)
         in_a = source_ranges(plan.rel_a, a._layout, sorted(set(m[1] for m in plan.matched)))
         in_b = source_ranges(plan.rel_b, b._layout, sorted(set(m[2] for m in plan.matched)))
-        out_c = merged([(plan.Lo.arena_off[m[0]], plan.Lo.arena_off[m[0]] + plan.Lo.rows[m[0]] * plan.Lo.cols[m[0]])
+        out_c = merged([(plan.Lo.arena_off[m[0]], plan.Lo.arena_off[m[0]] + plan.Lo.rows[m[0]] * plan.Lo.ld[m[0]])
                         for m in plan.matched])
     else:
         in_a, in_b = [(0, hA.numel())], [(0, hB.numel())]

@@ -83,7 +83,8 @@ int t10_fuse_qnums(int nbonds, int nsym, const int64_t* h_dims, const int32_t* h
  *   d_bra_map     [C, 2]           same for columns
  *   d_ket_idx     [R]              flat rows grouped by sector, ascending inside a sector
  *   d_bra_idx     [C]              same for columns
- *   d_sec_info    [cap_sec, 8]     {rows, cols, ket_start, bra_start, arena_off, 0,0,0}
+ *   d_sec_info    [cap_sec, 8]     {rows, cols, ket_start, bra_start, arena_off, ld, 0,0}; ld = cols rounded up
+ *                                  to even = leading dimension of the stored sector (16-byte aligned fp64 rows)
  *   d_rowbase     [R]              arena element offset of the row's first element, -1 if none
  *   d_coloff      [C]              column offset inside the sector, -1 if none
  *   h_counts      [4]              {nsec, arena_elems (incl. alignment padding), n_ket_phys, n_bra_phys}

@@ -211,7 +211,7 @@ class UniTensor:
                 raise RuntimeError("UniTensor.Storage: number of blocks changed")
             for b, v in enumerate(views):
                 x = bl[b]
-                if x.data_ptr() == v.data_ptr() and x.shape == v.shape and x.is_contiguous():
+                if x.data_ptr() == v.data_ptr() and x.shape == v.shape and x.stride() == v.stride():
                     continue
                 if tuple(x.shape) != tuple(v.shape):
                     raise RuntimeError("UniTensor.Storage[%d]: block of shape %s assigned where %s is required"

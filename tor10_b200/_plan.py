@@ -111,6 +111,7 @@ class BlockLayout:
         self.ket_start = info[:, 2].copy()
         self.bra_start = info[:, 3].copy()
         self.arena_off = info[:, 4].copy()
+        self.ld = info[:, 5].copy()          # leading dimension of the stored sector = cols rounded up to even
         self.nnz = int((self.rows * self.cols).sum())
         self._qindex = {tuple(q): i for i, q in enumerate(self.block_qnums.tolist())}
         self._host = {}
@@ -146,8 +147,9 @@ class BlockLayout:
         return (torch.zeros if zero else torch.empty)(n, device=self.device, dtype=dtype)
 
     def views(self, arena):
-        return [arena[int(o):int(o + r * c)].view(int(r), int(c))
-                for o, r, c in zip(self.arena_off, self.rows, self.cols)]
+        # [rows, cols] window of the [rows, ld] stored block (a strided view when cols is odd)
+        return [arena[int(o):int(o + r * l)].view(int(r), int(l))[:, :int(c)]
+                for o, r, c, l in zip(self.arena_off, self.rows, self.cols, self.ld)]
 
 
 def layout_signature(bonds, braket, rowrank):
@@ -175,7 +177,7 @@ class PackedLayout:
 
     @staticmethod
     def native(L):
-        return PackedLayout(L.arena_off, L.cols, L.arena_elems + ARENA_ALIGN)   # multiple of 16
+        return PackedLayout(L.arena_off, L.ld, L.arena_elems + ARENA_ALIGN)   # multiple of 16
 
     @staticmethod
     def padded(L):
@@ -563,15 +565,7 @@ class ContractPlan:
         self.matched = matched
         sec_a = sorted(set(m[1] for m in matched))
         sec_b = sorted(set(m[2] for m in matched))
-        want_aligned = a.dtype == torch.float64 and pick_tile_cfg(None) in ALIGNED_CFGS
-        if want_aligned:
-            # an operand read in place has leading dimension = its sector width; odd widths would force the
-            # whole group onto the predicated-loader kernel, so such an operand is copied once into the padded
-            # scratch layout by the relayout kernel (identity permutation)
-            if ident_a and any(int(La.cols[s]) % 2 for s in sec_a):
-                ident_a = False
-            if ident_b and any(int(Lb.cols[s]) % 2 for s in sec_b):
-                ident_b = False
+        # (stored sectors have an even leading dimension, so an operand read in place is always 16-byte aligned)
         self.rel_a = None if ident_a else get_relayout(Ma, La, map_a, padded=True, sectors=sec_a)
         self.rel_b = None if ident_b else get_relayout(Mb, Lb, map_b, padded=True, sectors=sec_b)
         pa = self.rel_a.packed if self.rel_a else PackedLayout.native(La)
@@ -579,7 +573,7 @@ class ContractPlan:
         prob = np.zeros(len(matched), dtype=_lib.GEMM_PROBLEM_DTYPE)
         for i, (ob, ab, bb) in enumerate(matched):
             prob[i] = (pa.off[ab], pb.off[bb], Lo.arena_off[ob], La.rows[ab], Lb.cols[bb], La.cols[ab],
-                       pa.ld[ab], pb.ld[bb], Lo.cols[ob])
+                       pa.ld[ab], pb.ld[bb], Lo.ld[ob])
         self.gemm = GemmGroup(prob, dev, a.dtype, sharded=shard is not None and shard[1] > 1)
         self.flops = self.gemm.flops
         self.gemm_bytes = self.gemm.bytes

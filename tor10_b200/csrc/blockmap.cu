@@ -270,7 +270,9 @@ __global__ void k_rank_scan(int32_t* __restrict__ hist, int64_t nseg, int64_t ns
   if (threadIdx.x == 0) totals[s] = carry_s;
 }
 
-// sec_info [nsec,8] = {rows, cols, ket_start, bra_start, arena_off, 0, 0, 0}
+// sec_info [nsec,8] = {rows, cols, ket_start, bra_start, arena_off, ld, 0, 0}
+// ld = cols rounded up to even: every stored row starts 16-byte aligned (fp64), so a sector can feed the
+// grouped GEMM's 16-byte cp.async loaders in place, whatever its width
 __global__ void k_sector_offsets(const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
                                  int64_t nsec, int64_t* __restrict__ sec_info,
                                  int64_t* __restrict__ counts) {
@@ -282,11 +284,13 @@ __global__ void k_sector_offsets(const int64_t* __restrict__ rows, const int64_t
     o[1] = cols[s];
     o[2] = ks;
     o[3] = bs;
+    const int64_t ld = cols[s] + (cols[s] & 1);
     o[4] = off;
-    o[5] = o[6] = o[7] = 0;
+    o[5] = ld;
+    o[6] = o[7] = 0;
     ks += rows[s];
     bs += cols[s];
-    int64_t sz = rows[s] * cols[s];
+    int64_t sz = rows[s] * ld;
     off += (sz + T10_ARENA_ALIGN - 1) / T10_ARENA_ALIGN * T10_ARENA_ALIGN;
   }
   counts[1] = off;
@@ -325,7 +329,7 @@ __global__ void k_rank_write(const int32_t* __restrict__ key, const int32_t* __r
         map[2 * x + 1] = off;
         if (is_row) {
           idx[si[2] + off] = x;
-          rowbase[x] = si[4] + off * si[1];
+          rowbase[x] = si[4] + off * si[5];
         } else {
           idx[si[3] + off] = x;
           coloff[x] = (int32_t)off;
