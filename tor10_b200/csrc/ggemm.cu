@@ -845,7 +845,10 @@ extern "C" int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_
         int64_t mm = std::min(bm, p.m - m0), nn = std::min(bn, p.n - n0);
         // cost model = DMMA count: k-steps x valid 8x8 fragments (ragged tiles skip empty fragments),
         // plus a fixed prologue/epilogue term worth about two full k-steps
-        int64_t frags = ((mm + 7) / 8) * ((nn + 7) / 8);
+        // (the aligned kernels 40 / 42 skip at warp-tile granularity, 32 x 32 resp. 32 x 64)
+        const int64_t gm = (tile_cfg == 40 || tile_cfg == 42) ? 32 : 8;
+        const int64_t gn = tile_cfg == 42 ? 64 : gm;
+        int64_t frags = ((mm + gm - 1) / gm) * (gm / 8) * ((nn + gn - 1) / gn) * (gn / 8);
         v.push_back({(int32_t)i, m0, n0, kt * (bk / 4) * frags + 2 * (bk / 4) * (bm / 8) * (bn / 8)});
       }
   }
