@@ -227,7 +227,7 @@ int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npee
 int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t n, const void* d_flags, int nflags,
                   uint64_t step, int32_t* d_err, t10_stream_t stream);
 
-/* Profiling aid: while d_trace != NULL the fp64 kernels 0..3 record, per tile t of the tile table,
+/* Profiling aid: while d_trace != NULL the fp64 tensor-core kernels record, per tile t of the tile table,
  * d_trace[4t..4t+3] = {SM id, CTA, globaltimer at start, globaltimer at end} (uint64).  NULL turns it off. */
 int t10_ggemm_set_trace(void* d_trace);
 

@@ -36,7 +36,8 @@ start = t0.min(); span = (t1.max() - start) * 1e-3
 dur = (t1 - t0) * 1e-3
 kk = pr["k"][tiles[:, 0]].astype(np.int64)
 mm = np.minimum(64, pr["m"][tiles[:, 0]] - tiles[:, 1]); nn = np.minimum(64, pr["n"][tiles[:, 0]] - tiles[:, 2])
-cost = (-(-kk // 16)) * 4 * (-(-mm // 8)) * (-(-nn // 8))       # DMMAs per warp-set
+gran = 32 if g.tile_cfg in (40, 42) else 8
+cost = (-(-kk // 16)) * 4 * (-(-mm // gran)) * (-(-nn // gran)) * (gran // 8) ** 2       # DMMAs per warp-set
 print("sched=%s cfg=%d tiles=%d span=%.1f us  sum(tile dur)=%.0f us  CTAs seen=%d SMs seen=%d"
       % (os.environ.get("TOR10_GGEMM_SCHED", "slots"), g.tile_cfg, g.ntiles, span, dur.sum(), len(set(cta)), len(set(sm))))
 # per-SM: union of busy intervals, last end

@@ -444,7 +444,8 @@ template <class Cfg, int MIN_CTAS>
 __global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
 k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbase,
                double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
-               int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start) {
+               int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start,
+               unsigned long long* __restrict__ trace) {
   static_assert(Cfg::BK == 16, "four k-groups per stage");
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
@@ -474,6 +475,15 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
     const int m_rem = p.m - m0, n_rem = p.n - n0;
     const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
     const bool active = (m_rem > wm0) && (n_rem > wn0);
+    if (trace != nullptr && threadIdx.x == 0) {   // profiling aid (t10_ggemm_set_trace)
+      unsigned smid;
+      unsigned long long now;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[4 * t + 0] = smid;
+      trace[4 * t + 1] = blockIdx.x;
+      trace[4 * t + 2] = now;
+    }
     // per-thread source pointers; rows beyond m and column chunks beyond n are clamped (never stored)
     const double* pa[A_PASSES];
 #pragma unroll
@@ -552,6 +562,11 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
     }
     cp_async_wait<0>();
 
+    if (trace != nullptr && threadIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[4 * t + 3] = now;
+    }
     if (!active) continue;
     double* C = Cbase + p.c_off;
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
@@ -772,7 +787,7 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
