@@ -13,6 +13,7 @@
 // FP32: tile_cfg 50 (default) = tcgen05 / TMEM kind::tf32 three-pass split, ggemm_tf32.cu;
 // tile_cfg 0 / 100 = SIMT register-tiled fp32 FMA kernel (comparison path).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -849,6 +850,18 @@ extern "C" int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_
   int bm, bn, bk;
   T10_REQUIRE(tile_dims(tile_cfg, &bm, &bn, &bk), T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
   struct Tl { int32_t p, m0, n0; int64_t cost; };
+  const int64_t fixed_steps = 2;
+  const char* al = getenv("TOR10_GGEMM_ALPHA");
+  const int64_t alpha = al ? atoll(al) : 75;     // measured on C3a: 0 -> 118.1 us, 50 -> 120.3, 75 -> 112.3, 100 -> 114.4
+  const bool warp_granular = tile_cfg == 40 || tile_cfg == 42;
+  int wmd = bm, wnd = bn;          // warp tile of the kernel
+  switch (tile_cfg) {
+    case 0: case 3: case 40: wmd = 32; wnd = 32; break;
+    case 1: case 2: wmd = 64; wnd = 32; break;
+    case 8: wmd = 16; wnd = 16; break;
+    case 42: wmd = 32; wnd = 64; break;
+    default: break;
+  }
   std::vector<Tl> v;
   for (int64_t i = 0; i < nprob; ++i) {
     const t10_gemm_problem& p = h_prob[i];
@@ -858,13 +871,23 @@ extern "C" int t10_ggemm_plan_tiles(int tile_cfg, int64_t nprob, const t10_gemm_
     for (int m0 = 0; m0 < p.m; m0 += bm)
       for (int n0 = 0; n0 < p.n; n0 += bn) {
         int64_t mm = std::min(bm, p.m - m0), nn = std::min(bn, p.n - n0);
-        // cost model = DMMA count: k-steps x valid 8x8 fragments (ragged tiles skip empty fragments),
-        // plus a fixed prologue/epilogue term worth about two full k-steps
-        // (the aligned kernels 40 / 42 skip at warp-tile granularity, 32 x 32 resp. 32 x 64)
-        const int64_t gm = (tile_cfg == 40 || tile_cfg == 42) ? 32 : 8;
-        const int64_t gn = tile_cfg == 42 ? 64 : gm;
-        int64_t frags = ((mm + gm - 1) / gm) * (gm / 8) * ((nn + gn - 1) / gn) * (gn / 8);
-        v.push_back({(int32_t)i, m0, n0, kt * (bk / 4) * frags + 2 * (bk / 4) * (bm / 8) * (bn / 8)});
+        // Cost model.  Each warp of a CTA sits on its own scheduler, so a k-step lasts as long as its BUSIEST
+        // warp's DMMAs (x16 cycles), not their sum: a ragged tile with one full warp tile costs what a full
+        // tile costs.  cost = k-steps x (alpha * busiest warp's fragments * warps + (1 - alpha) * all valid
+        // fragments) + a fixed prologue/epilogue term.  The general kernels skip invalid 8x8 fragments; the
+        // aligned kernels (40, 42) skip whole warp tiles only.
+        int64_t wmax = 0, frags = 0;
+        for (int wm0 = 0; wm0 < bm; wm0 += wmd)
+          for (int wn0 = 0; wn0 < bn; wn0 += wnd) {
+            int64_t mi = std::max<int64_t>(0, std::min<int64_t>(wmd / 8, (mm - wm0 + 7) / 8));
+            int64_t ni = std::max<int64_t>(0, std::min<int64_t>(wnd / 8, (nn - wn0 + 7) / 8));
+            if (warp_granular && mi > 0 && ni > 0) { mi = wmd / 8; ni = wnd / 8; }
+            wmax = std::max(wmax, mi * ni);
+            frags += mi * ni;
+          }
+        const int64_t nwarps = (bm / wmd) * (bn / wnd);
+        const int64_t per_step = (alpha * wmax * nwarps + (100 - alpha) * frags) / 100;
+        v.push_back({(int32_t)i, m0, n0, kt * (bk / 4) * per_step + fixed_steps * (bk / 4) * (bm / 8) * (bn / 8)});
       }
   }
   std::stable_sort(v.begin(), v.end(), [](const Tl& a, const Tl& b) { return a.cost > b.cost; });
