@@ -359,17 +359,15 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
       42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned groups of at least four waves of
           such tiles (large dense GEMMs);
       8   32x32 tiles for a rank of a sector-sharded contraction left with fewer than 1.5 64x64 tiles per SM
-          (C3a on 8 GPUs: 53.5 us -> 39.6 us); sharded groups otherwise stay on 3 (fused all-gather epilogue)."""
+          (C3a on 8 GPUs: 53.5 us -> 39.6 us)."""
     forced = os.environ.get("TOR10_GGEMM_CFG")
     if forced is not None:
         return int(forced)
     if problems is None or not len(problems):
         return 3
     m, n = problems["m"].astype(np.int64), problems["n"].astype(np.int64)
-    if sharded:
-        if int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count():
-            return 8
-        return 3
+    if sharded and int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count():
+        return 8
     aligned = base_aligned and bool(((problems["lda"] % 2 == 0) & (problems["ldb"] % 2 == 0)
                                      & (problems["a_off"] % 2 == 0) & (problems["b_off"] % 2 == 0)).all())
     if not aligned:
@@ -386,7 +384,7 @@ def _sm_count():
 
 
 ALIGNED_CFGS = (40, 42)   # kernels that require 16-byte aligned operand rows
-FUSABLE_CFGS = (0, 1, 2, 3, 8)   # kernels with the fused all-gather epilogue and the counter schedules
+FUSABLE_CFGS = (0, 1, 2, 3, 8, 40, 42)   # kernels with the fused all-gather epilogue
 FALLBACK_CFG = 3
 
 

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, MIN_CTAS)
 k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbase,
                double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
                int64_t ntiles, const int4* __restrict__ tiles, const int32_t* __restrict__ slot_start,
-               unsigned long long* __restrict__ trace) {
+               unsigned long long* __restrict__ trace, const __grid_constant__ PeerOut peers) {
   static_assert(Cfg::BK == 16, "four k-groups per stage");
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
@@ -568,6 +568,38 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       trace[4 * t + 3] = now;
     }
+    if (peers.n > 0) {
+      // fused all-gather (see k_ggemm_f64): registers -> shared tile -> row-contiguous stores to every rank
+      constexpr int CLD = Cfg::BN + 2;
+      static_assert(Cfg::BM * CLD <= Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE), "C tile must fit the stage memory");
+      __syncthreads();   // every warp is done reading the last stage
+      double* Cs = smem;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+          for (int j = 0; j < Cfg::NI; ++j)
+            *reinterpret_cast<double2*>(Cs + (wm0 + i * 8 + g) * CLD + wn0 + j * 8 + 2 * tig) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+      __syncthreads();
+      bool p16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0);
+      for (int q = 0; q < peers.n; ++q) p16 = p16 && (((uintptr_t)peers.ptr[q] & 15) == 0);
+      for (int idx = threadIdx.x; idx < Cfg::BM * (Cfg::BN / 2); idx += Cfg::THREADS) {
+        const int r = idx / (Cfg::BN / 2), c = (idx % (Cfg::BN / 2)) * 2;
+        if (m0 + r >= p.m || n0 + c >= p.n) continue;
+        const double2 v = *reinterpret_cast<const double2*>(Cs + r * CLD + c);
+        const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
+        const bool two = n0 + c + 1 < p.n;
+#pragma unroll 1
+        for (int q = 0; q < peers.n; ++q) {
+          double* o = peers.ptr[q] + off;
+          if (two && p16) *reinterpret_cast<double2*>(o) = v;
+          else { o[0] = v.x; if (two) o[1] = v.y; }
+        }
+      }
+      continue;   // the barrier that opens the next tile orders these shared reads before the next loads
+    }
     if (!active) continue;
     double* C = Cbase + p.c_off;
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
@@ -585,6 +617,19 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
         } else if (c < p.n) {
           o[0] = acc[i][j][0];
         }
+      }
+    }
+  }
+  if (peers.n > 0 && peers.done_ctr != nullptr) {
+    __syncthreads();   // every thread's tile stores precede thread 0's fence
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(peers.done_ctr, 1) == (int)gridDim.x - 1) {
+        *peers.done_ctr = 0;
+        __threadfence_system();
+        for (int q = 0; q < peers.n; ++q)
+          if (peers.flag[q] != nullptr)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[q]), "l"(peers.step) : "memory");
       }
     }
   }
@@ -765,7 +810,7 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
 template <class Cfg, int MIN_CTAS>
 static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const double* B, double* C,
                          const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
-                         const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st) {
+                         const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64_v5<Cfg, MIN_CTAS>;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
@@ -788,7 +833,8 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace,
+                                                    peers);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -797,15 +843,16 @@ static int dispatch_f64(int tile_cfg, bool launch, int* nslots_out, const double
                         const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
                         const int32_t* slot_start, int32_t* sched, cudaStream_t st,
                         const PeerOut& peers = PeerOut{}) {
-  if (peers.n > 0) T10_REQUIRE((tile_cfg >= 0 && tile_cfg <= 3) || tile_cfg == 8, T10_ERR_INVALID, "fused all-gather needs fp64 kernels 0..3 or 8");
+  if (peers.n > 0) T10_REQUIRE((tile_cfg >= 0 && tile_cfg <= 3) || tile_cfg == 8 || tile_cfg == 40 || tile_cfg == 42, T10_ERR_INVALID,
+                             "fused all-gather needs an fp64 tensor-core kernel (0..3, 8, 40, 42)");
   switch (tile_cfg) {
     case 0: return launch_f64<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     case 1: return launch_f64<CfgB, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     case 2: return launch_f64<CfgC, 1>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     case 3: return launch_f64<CfgD, 3>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     case 8: return launch_f64<CfgS, 4>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
-    case 40: return launch_f64_v5<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
-    case 42: return launch_f64_v5<CfgL, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st);
+    case 40: return launch_f64_v5<CfgA, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
+    case 42: return launch_f64_v5<CfgL, 2>(launch, nslots_out, A, B, C, prob, ntiles, tiles, nslots, slot_start, sched, st, peers);
     default: T10_REQUIRE(false, T10_ERR_INVALID, "unknown tile_cfg %d", tile_cfg);
   }
 }
