@@ -210,6 +210,12 @@ int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d
               const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
               int32_t* d_sched, t10_stream_t stream);
 
+/* Deterministic second half of a split-K product: d_out[i] = sum_{s < nslices} d_ws[s * n + i], added in slice
+ * order.  A GEMM whose output is a handful of tiles but whose K is long (the norms and expectation values of
+ * iTEBD.py: [1 x 4096] x [4096 x 1]) is issued as `nslices` problems of one t10_ggemm launch, each writing its
+ * partial product to slice s of a workspace, instead of one CTA walking the whole K alone.               */
+int t10_reduce_slices(int dtype, const void* d_ws, void* d_out, int64_t n, int nslices, t10_stream_t stream);
+
 /* Fused grouped GEMM -> all-gather (fp64, kernels 0..3; multi-GPU sector sharding, no reference counterpart:
  * the reference is single-device).  Same as t10_ggemm, but every output tile is stored into ALL `npeers`
  * arenas h_peer_C[0..npeers) -- this rank's staging arena and the peers', mapped through NVLink peer memory

@@ -1061,14 +1061,35 @@ def _dense_gemm(A2, B2):
     if K == 0:
         return out.zero_()
     base_ok = (A2.data_ptr() % 16 == 0) and (B2.data_ptr() % 16 == 0)
+    # split-K: a product with a handful of output tiles and a long K (norms, expectation values) would keep ONE
+    # CTA busy for its whole K (a [1,4096] x [4096,1] dot: 191 us); it is issued as `nsl` K-slices of one grouped
+    # launch writing partial products to a workspace, summed in slice order by t10_reduce_slices (deterministic).
+    ntile = ((M + 63) // 64) * ((N + 63) // 64)
+    nsl = 1
+    if ntile <= 16 and K >= 1024:
+        nsl = max(1, min((K + 255) // 256, 296 // ntile))
     key = (M, N, K, A2.dtype, A2.device.index, base_ok)
     grp = _GEMM_GROUPS.get(key)
     if grp is None:
-        prob = np.zeros(1, dtype=_lib.GEMM_PROBLEM_DTYPE)
-        prob[0] = (0, 0, 0, M, N, K, K, N, N)
+        if nsl > 1:
+            ks = ((K + nsl - 1) // nsl + 15) // 16 * 16
+            nsl = (K + ks - 1) // ks
+            prob = np.zeros(nsl, dtype=_lib.GEMM_PROBLEM_DTYPE)
+            for s_ in range(nsl):
+                prob[s_] = (s_ * ks, s_ * ks * N, s_ * M * N, M, N, min(ks, K - s_ * ks), K, N, N)
+        else:
+            prob = np.zeros(1, dtype=_lib.GEMM_PROBLEM_DTYPE)
+            prob[0] = (0, 0, 0, M, N, K, K, N, N)
         grp = _plan.GemmGroup(prob, A2.device, A2.dtype, base_aligned=base_ok)
+        grp.nslices = len(prob)
         _GEMM_GROUPS[key] = grp
-    grp.run(A2, B2, out)
+    if grp.nslices > 1:
+        ws = torch.empty((grp.nslices, M, N), device=A2.device, dtype=A2.dtype)
+        grp.run(A2, B2, ws)
+        _lib.check(_lib.load().t10_reduce_slices(_lib.dtype_code(A2.dtype), ws.data_ptr(), out.data_ptr(), M * N,
+                                                 grp.nslices, _lib.stream_ptr()))
+    else:
+        grp.run(A2, B2, out)
     return out
 
 

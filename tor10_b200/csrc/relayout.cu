@@ -438,6 +438,30 @@ extern "C" int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int
   return T10_OK;
 }
 
+// out[i] = sum over slices s (in order) of ws[s * n + i]: the deterministic second half of a split-K product
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_reduce_slices(const T* __restrict__ ws, T* __restrict__ out, int64_t n, int nslices) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T acc = ws[i];
+    for (int s2 = 1; s2 < nslices; ++s2) acc += ws[(int64_t)s2 * n + i];
+    out[i] = acc;
+  }
+}
+
+extern "C" int t10_reduce_slices(int dtype, const void* d_ws, void* d_out, int64_t n, int nslices,
+                                 t10_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  T10_REQUIRE(n >= 0 && nslices >= 1, T10_ERR_INVALID, "reduce_slices: bad sizes");
+  if (n == 0) return T10_OK;
+  unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
+  if (dtype == T10_F64) k_reduce_slices<double><<<grid, 256, 0, st>>>((const double*)d_ws, (double*)d_out, n, nslices);
+  else if (dtype == T10_F32) k_reduce_slices<float><<<grid, 256, 0, st>>>((const float*)d_ws, (float*)d_out, n, nslices);
+  else T10_REQUIRE(false, T10_ERR_UNSUPPORTED, "reduce_slices: dtype %d not supported", dtype);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
 extern "C" int t10_relayout_runs(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_runs,
                                  int64_t nruns, const int32_t* d_chunk_first, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
