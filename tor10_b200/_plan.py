@@ -180,9 +180,15 @@ class PackedLayout:
         return PackedLayout(L.arena_off, L.ld, L.arena_elems + ARENA_ALIGN)   # multiple of 16
 
     @staticmethod
-    def padded(L):
+    def padded(L, sectors=None):
+        """Scratch layout; with `sectors` only those sectors get space (a rank of a sharded contraction relays
+        out 1/world of the tensor: the buffer and the element index shrink accordingly)."""
         ld = (L.cols + 1) // 2 * 2
         sz = (L.rows * ld + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+        if sectors is not None:
+            keep = np.zeros(L.nsec, dtype=bool)
+            keep[list(sectors)] = True
+            sz = np.where(keep, sz, 0)
         off = np.zeros(L.nsec, dtype=np.int64)
         off[1:] = np.cumsum(sz)[:-1]
         return PackedLayout(off, ld, int(sz.sum()) + ARENA_ALIGN)
@@ -332,7 +338,7 @@ def get_relayout(M, L, mapper, padded=False, sectors=None):
     key = (M.key, L.key, tuple(int(x) for x in mapper), bool(padded), None if sectors is None else tuple(sectors))
     pl = _RELAYOUTS.get(key)
     if pl is None:
-        packed = PackedLayout.padded(L) if padded else PackedLayout.native(L)
+        packed = PackedLayout.padded(L, sectors) if padded else PackedLayout.native(L)
         pl = RelayoutPlan(M, L, mapper, packed, sectors)
         _RELAYOUTS[key] = pl
     return pl
