@@ -390,7 +390,7 @@ def _sm_count():
 
 
 ALIGNED_CFGS = (40, 42)   # kernels that require 16-byte aligned operand rows
-FUSABLE_CFGS = (0, 1, 2, 3, 8, 40, 42)   # kernels with the fused all-gather epilogue
+FUSABLE_CFGS = (0, 2, 3, 8, 40, 42)   # kernels with the fused all-gather epilogue
 FALLBACK_CFG = 3
 
 

@@ -352,31 +352,49 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
     // epilogue: lane holds C[row g][cols 2*tig, 2*tig+1] of every 8x8 fragment
     const bool c16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)Cbase & 15) == 0);
     if (peers.n > 0) {
-      // fused all-gather: registers -> shared tile -> row-contiguous 16-byte stores into every rank's arena
+      // Fused all-gather: registers -> a dedicated shared tile -> one TMA bulk copy (cp.async.bulk, shared ->
+      // global) per tile row and rank, issued by warp 0 and left in flight while the CTA computes its next
+      // tile.  The copy engine streams whole rows over NVLink; no LSU stores, no registers.
       constexpr int CLD = Cfg::BN + 2;
-      static_assert(Cfg::BM * CLD <= Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE), "C tile must fit the stage memory");
-      __syncthreads();   // every warp is done reading the last stage
-      double* Cs = smem;
+      double* Cs = smem + Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE);
+      if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left Cs
+      __syncthreads();
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
         for (int j = 0; j < Cfg::NI; ++j)
           *reinterpret_cast<double2*>(Cs + (wm0 + i * 8 + g) * CLD + wn0 + j * 8 + 2 * tig) =
               make_double2(acc[i][j][0], acc[i][j][1]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async-proxy reads
       __syncthreads();
       bool p16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0);
       for (int q = 0; q < peers.n; ++q) p16 = p16 && (((uintptr_t)peers.ptr[q] & 15) == 0);
-      for (int idx = threadIdx.x; idx < Cfg::BM * (Cfg::BN / 2); idx += Cfg::THREADS) {
-        const int r = idx / (Cfg::BN / 2), c = (idx % (Cfg::BN / 2)) * 2;
-        if (m0 + r >= p.m || n0 + c >= p.n) continue;
-        const double2 v = *reinterpret_cast<const double2*>(Cs + r * CLD + c);
-        const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
-        const bool two = n0 + c + 1 < p.n;
+      const int rows = min(Cfg::BM, m_rem), cols = min(Cfg::BN, n_rem);
+      if (p16) {
+        if (warp == 0) {
+          const unsigned bytes = (unsigned)(cols & ~1) * 8u;
+          for (int r = lane; r < rows; r += 32) {
+            const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(Cs + r * CLD);
 #pragma unroll 1
-        for (int q = 0; q < peers.n; ++q) {
-          double* o = peers.ptr[q] + off;
-          if (two && p16) *reinterpret_cast<double2*>(o) = v;
-          else { o[0] = v.x; if (two) o[1] = v.y; }
+            for (int q = 0; q < peers.n; ++q) {
+              double* o = peers.ptr[q] + off;
+              if (bytes)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o), "r"(src), "r"(bytes)
+                             : "memory");
+              if (cols & 1) o[cols - 1] = Cs[r * CLD + cols - 1];
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::THREADS) {
+          const int r = idx / Cfg::BN, c = idx % Cfg::BN;
+          if (r >= rows || c >= cols) continue;
+          const double v = Cs[r * CLD + c];
+          const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
+#pragma unroll 1
+          for (int q = 0; q < peers.n; ++q) peers.ptr[q][off] = v;
         }
       }
     } else {
@@ -411,8 +429,15 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
     }
     __syncthreads();  // stages free for the next tile; next tile index visible
   }
+  if (peers.n > 0) {   // the bulk copies still in flight must have landed before this rank signals
+    if (warp == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+  }
   if (peers.n > 0 && peers.done_ctr != nullptr && threadIdx.x == 0) {
-    // every thread's tile stores are ordered before this point by the CTA barrier that ends each tile
+    // every thread's tile stores are ordered before this point by the CTA barrier above
     __threadfence_system();
     if (atomicAdd(peers.done_ctr, 1) == (int)gridDim.x - 1) {
       *peers.done_ctr = 0;
@@ -569,11 +594,13 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
       trace[4 * t + 3] = now;
     }
     if (peers.n > 0) {
-      // fused all-gather (see k_ggemm_f64): registers -> shared tile -> row-contiguous stores to every rank
+      // Fused all-gather: registers -> a dedicated shared tile -> one TMA bulk copy (cp.async.bulk, shared ->
+      // global) per tile row and rank, issued by warp 0 and left in flight while the CTA computes its next
+      // tile.  The copy engine streams whole 512-byte rows over NVLink; no LSU stores, no registers.
       constexpr int CLD = Cfg::BN + 2;
-      static_assert(Cfg::BM * CLD <= Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE), "C tile must fit the stage memory");
-      __syncthreads();   // every warp is done reading the last stage
-      double* Cs = smem;
+      double* Cs = smem + Cfg::STAGES * (Cfg::A_STAGE + Cfg::B_STAGE);
+      if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left Cs
+      __syncthreads();
       if (active) {
 #pragma unroll
         for (int i = 0; i < Cfg::MI; ++i)
@@ -581,24 +608,40 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
           for (int j = 0; j < Cfg::NI; ++j)
             *reinterpret_cast<double2*>(Cs + (wm0 + i * 8 + g) * CLD + wn0 + j * 8 + 2 * tig) =
                 make_double2(acc[i][j][0], acc[i][j][1]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async-proxy reads
       }
       __syncthreads();
       bool p16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0);
       for (int q = 0; q < peers.n; ++q) p16 = p16 && (((uintptr_t)peers.ptr[q] & 15) == 0);
-      for (int idx = threadIdx.x; idx < Cfg::BM * (Cfg::BN / 2); idx += Cfg::THREADS) {
-        const int r = idx / (Cfg::BN / 2), c = (idx % (Cfg::BN / 2)) * 2;
-        if (m0 + r >= p.m || n0 + c >= p.n) continue;
-        const double2 v = *reinterpret_cast<const double2*>(Cs + r * CLD + c);
-        const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
-        const bool two = n0 + c + 1 < p.n;
+      const int rows = min(Cfg::BM, m_rem), cols = min(Cfg::BN, n_rem);
+      if (p16) {
+        if (warp == 0) {
+          const unsigned bytes = (unsigned)(cols & ~1) * 8u;
+          for (int r = lane; r < rows; r += 32) {
+            const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(Cs + r * CLD);
 #pragma unroll 1
-        for (int q = 0; q < peers.n; ++q) {
-          double* o = peers.ptr[q] + off;
-          if (two && p16) *reinterpret_cast<double2*>(o) = v;
-          else { o[0] = v.x; if (two) o[1] = v.y; }
+            for (int q = 0; q < peers.n; ++q) {
+              double* o = peers.ptr[q] + off;
+              if (bytes)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o), "r"(src), "r"(bytes)
+                             : "memory");
+              if (cols & 1) o[cols - 1] = Cs[r * CLD + cols - 1];
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::THREADS) {
+          const int r = idx / Cfg::BN, c = idx % Cfg::BN;
+          if (r >= rows || c >= cols) continue;
+          const double v = Cs[r * CLD + c];
+          const int64_t off = p.c_off + (int64_t)(m0 + r) * p.ldc + n0 + c;
+#pragma unroll 1
+          for (int q = 0; q < peers.n; ++q) peers.ptr[q][off] = v;
         }
       }
-      continue;   // the barrier that opens the next tile orders these shared reads before the next loads
+      continue;
     }
     if (!active) continue;
     double* C = Cbase + p.c_off;
@@ -618,6 +661,12 @@ k_ggemm_f64_v5(const double* __restrict__ Abase, const double* __restrict__ Bbas
           o[0] = acc[i][j][0];
         }
       }
+    }
+  }
+  if (peers.n > 0) {   // the bulk copies still in flight must have landed before this rank signals
+    if (warp == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
     }
   }
   if (peers.n > 0 && peers.done_ctr != nullptr) {
@@ -777,9 +826,13 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
                       const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
                       const int32_t* slot_start, int32_t* sched, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64<Cfg, MIN_CTAS, RAGGED>;
+  constexpr int PEER_TILE_BYTES = Cfg::BM * (Cfg::BN + 2) * 8;   // staging tile of the fused all-gather
+  constexpr bool PEER_FITS = Cfg::SMEM_BYTES + PEER_TILE_BYTES <= 227 * 1024;
+  T10_REQUIRE(peers.n == 0 || PEER_FITS, T10_ERR_UNSUPPORTED, "fused all-gather: tile configuration too large");
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES + (PEER_FITS ? PEER_TILE_BYTES : 0)));
     int occ = 0;
     T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
@@ -801,8 +854,8 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched,
-                                                    nbins, g_trace, peers);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES + (peers.n > 0 ? PEER_TILE_BYTES : 0), st>>>(
+      A, B, C, prob, ntiles, (const int4*)tiles, slot_start, sched, nbins, g_trace, peers);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -812,9 +865,13 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
                          const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
                          const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64_v5<Cfg, MIN_CTAS>;
+  constexpr int PEER_TILE_BYTES = Cfg::BM * (Cfg::BN + 2) * 8;   // staging tile of the fused all-gather
+  constexpr bool PEER_FITS = Cfg::SMEM_BYTES + PEER_TILE_BYTES <= 227 * 1024;
+  T10_REQUIRE(peers.n == 0 || PEER_FITS, T10_ERR_UNSUPPORTED, "fused all-gather: tile configuration too large");
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::SMEM_BYTES + (PEER_FITS ? PEER_TILE_BYTES : 0)));
     int occ = 0;
     T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
@@ -833,8 +890,8 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace,
-                                                    peers);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES + (peers.n > 0 ? PEER_TILE_BYTES : 0), st>>>(
+      A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace, peers);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
