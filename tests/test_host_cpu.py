@@ -84,6 +84,21 @@ def test_no_cpu_compute_path(T):
         T.Matmul(x, y)
 
 
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no file of the package (or the example script) may import it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("tor10_b200", "examples"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+
+
 def test_bond_matches_reference_goldens(T, golden):
     z, specs = golden("bond")
     for key, sp in specs.items():
