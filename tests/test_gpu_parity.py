@@ -237,7 +237,7 @@ def test_contract_sym_goldens(T, golden):
             assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "8", "40", "42", "100"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "8", "40", "42", "46", "100"])
 def test_contract_c3a_small_all_tile_shapes(T, cfg, monkeypatch):
     """C3a at chi=192 with every GEMM tile configuration (+ the SIMT cross-check kernel) vs the oracle."""
     monkeypatch.setenv("TOR10_GGEMM_CFG", cfg)

@@ -389,8 +389,8 @@ def _sm_count():
     return int(nsm.value)
 
 
-ALIGNED_CFGS = (40, 42)   # kernels that require 16-byte aligned operand rows
-FUSABLE_CFGS = (0, 2, 3, 8, 40, 42)   # kernels with the fused all-gather epilogue
+ALIGNED_CFGS = (40, 42, 46)   # kernels that require 16-byte aligned operand rows
+FUSABLE_CFGS = (0, 2, 3, 8, 40, 42, 46)   # kernels with the fused all-gather epilogue
 FALLBACK_CFG = 3
 
 
