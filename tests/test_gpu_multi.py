@@ -1,5 +1,6 @@
 """Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): a Contract whose sectors are sharded over
-2 ranks (NCCL gather) equals the single-GPU result bit for bit and the oracle within 1e-12."""
+2 ranks gives bit-identical results through every transport, equals the single-GPU result to rounding (1e-14)
+and the oracle within 1e-12."""
 import os
 import socket
 
@@ -35,13 +36,20 @@ def _worker(rank, world, port, q):
     b32 = psym(T, B, seed=42, device="cuda:%d" % rank, dtype=torch.float32)
     single32 = T.Contract(a32, b32)
     oc = orc.contract_sym(osym(A, seed=41), osym(B, seed=42))
-    same, err = True, 0.0
-    # every transport, three calls each (the staging arenas are double-buffered); "auto" = fused GEMM+all-gather
+    same, err, first = True, 0.0, None
+    # every transport, three calls each (the staging arenas are double-buffered); "auto" = fused GEMM+all-gather.
+    # All transports run the same kernels on the same sector shards: their results are bit-identical.  The
+    # single-GPU result may come from the stream-K schedule (another, equally fixed, summation split of k), so
+    # it is compared at rounding level.
     for transport in ("auto", "fused", "p2p", "nccl"):
         parallel.enable(transport=transport)
         for _ in range(3):
             sharded = T.Contract(a, b)
-            same = same and all(torch.equal(x, y) for x, y in zip(single.Storage, sharded.Storage))
+            if first is None:
+                first = [x.clone() for x in sharded.Storage]
+            same = same and all(torch.equal(x, y) for x, y in zip(first, sharded.Storage))
+            same = same and all(float((x - y).abs().max()) <= 1e-14 * float(x.abs().max())
+                                for x, y in zip(single.Storage, sharded.Storage))
             err = max(err, max(rel_err(x.cpu().numpy(), y) for x, y in zip(sharded.Storage, oc.blocks)))
         sh32 = T.Contract(a32, b32)      # fp32 plans cannot fuse: pull path
         same = same and all(torch.equal(x, y) for x, y in zip(single32.Storage, sh32.Storage))
@@ -67,5 +75,5 @@ def test_sharded_contract_two_gpus():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, same, err in res:
-        assert same, "rank %d: sharded result differs from the single-GPU result" % rank
+        assert same, "rank %d: transports disagree, or sharded result differs from the single-GPU result" % rank
         assert err <= 1e-12

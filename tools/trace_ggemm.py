@@ -20,14 +20,16 @@ g = plan.gemm
 for _ in range(3):
     T.Contract(a, b)
 torch.cuda.synchronize()
-trace = torch.zeros((g.ntiles, 4), dtype=torch.int64, device=dev)
+sk = getattr(g, "streamk", False)
+ntl = g.sk_npieces if sk else g.ntiles
+trace = torch.zeros((ntl, 4), dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.t10_ggemm_set_trace(trace.data_ptr())
 T.Contract(a, b)
 torch.cuda.synchronize()
 lib.t10_ggemm_set_trace(None)
 tr = trace.cpu().numpy()
-tiles = g.d_tiles.cpu().numpy()[: g.ntiles]
+tiles = (g.d_sk_tiles if sk else g.d_tiles).cpu().numpy()[:ntl]
 pr = g.problems
 sm, cta, t0, t1 = tr[:, 0], tr[:, 1], tr[:, 2], tr[:, 3]
 ok = t1 > 0
@@ -36,10 +38,15 @@ start = t0.min(); span = (t1.max() - start) * 1e-3
 dur = (t1 - t0) * 1e-3
 kk = pr["k"][tiles[:, 0]].astype(np.int64)
 mm = np.minimum(64, pr["m"][tiles[:, 0]] - tiles[:, 1]); nn = np.minimum(64, pr["n"][tiles[:, 0]] - tiles[:, 2])
-gran = 32 if g.tile_cfg in (40, 42) else 8
+gran = 32 if g.tile_cfg in (40, 42, 46) else 8
 cost = (-(-kk // 16)) * 4 * (-(-mm // gran)) * (-(-nn // gran)) * (gran // 8) ** 2       # DMMAs per warp-set
+if g.tile_cfg == 46:      # mixed shapes: every tile is four warp tiles wide; cost = k-steps x 64 fragments x 4
+    cost = (-(-kk // 16)) * 4 * 64
+if sk:
+    pcs = g.d_sk_pieces.cpu().numpy()
+    cost = (pcs[:, 1] - pcs[:, 0]).astype(np.int64) * 4 * 64
 print("sched=%s cfg=%d tiles=%d span=%.1f us  sum(tile dur)=%.0f us  CTAs seen=%d SMs seen=%d"
-      % (os.environ.get("TOR10_GGEMM_SCHED", "slots"), g.tile_cfg, g.ntiles, span, dur.sum(), len(set(cta)), len(set(sm))))
+      % (("stream-K" if sk else os.environ.get("TOR10_GGEMM_SCHED", "slots")), g.tile_cfg, ntl, span, dur.sum(), len(set(cta)), len(set(sm))))
 # per-SM: union of busy intervals, last end
 sm_end = {}; sm_work = {}
 for s_, e_, c_ in zip(sm, t1, cost):

@@ -362,8 +362,11 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
       40  same tile on the software-pipelined aligned-only kernel, 2 CTAs/SM: 33 TF against 30.6 TF in steady
           state, C3a GEMM stage 123.9 us -- taken when every operand row is 16-byte aligned AS STORED (an
           extra copy of an operand just to align it costs more than it gains);
-      42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned groups of at least four waves of
-          such tiles (large dense GEMMs);
+      42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned single GEMMs of at least four waves
+          of such tiles (large dense GEMMs);
+      46  the same main loop with mixed tile shapes (64x64 + 32x128 / 128x32 edge strips) for aligned GROUPS
+          (block-sparse contractions), run as stream-K when every CTA gets at least 16 k-steps (C3a GEMM stage
+          114.7 -> 110.9 us);
       8   32x32 tiles for a rank of a sector-sharded contraction left with fewer than 1.5 64x64 tiles per SM
           (C3a on 8 GPUs: 53.5 us -> 39.6 us)."""
     forced = os.environ.get("TOR10_GGEMM_CFG")
@@ -378,6 +381,10 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
                                      & (problems["a_off"] % 2 == 0) & (problems["b_off"] % 2 == 0)).all())
     if not aligned:
         return 3
+    if sharded:
+        return 40      # with the fused all-gather's staging tile the mixed kernel would drop to one CTA per SM
+    if len(problems) > 1:
+        return 46
     if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
         return 42
     return 40
@@ -448,9 +455,103 @@ class GemmGroup:
         self.d_slots = torch.from_numpy(slots).to(device) if self.nslots else None
         self.d_prob = torch.from_numpy(self.problems.view(np.uint8).reshape(-1)).to(device) if self.nprob else \
             torch.zeros(48, dtype=torch.uint8, device=device)
+        self.streamk = False
+        if (dtype == torch.float64 and self.tile_cfg == 46 and not sharded and self.ntiles > 0
+                and os.environ.get("TOR10_GGEMM_STREAMK", "1") == "1"):
+            self.streamk = self.build_streamk(int(ns.value))
         self.flops = float(sum(2.0 * int(p["m"]) * int(p["n"]) * int(p["k"]) for p in self.problems))
         self.bytes = float(sum(int(p["m"]) * int(p["k"]) + int(p["k"]) * int(p["n"]) + int(p["m"]) * int(p["n"])
                                for p in self.problems))
+
+    # ---- stream-K on the mixed-shape kernel: balance k-steps, not tiles -------------------------------------
+    def build_streamk(self, nslots):
+        """Cut the tile list (t10_ggemm_plan_tiles, cfg 46, heaviest first) into `nslots` equal shares of k-steps
+        (a k-step of the aligned kernel costs the same whatever the tile's raggedness; +2 per piece for the
+        pipeline fill).  A tile cut across CTAs becomes pieces: the CTAs holding its leading k-ranges park partial
+        sums, the one holding its last k-step adds them in order and stores the tile (t10_ggemm_streamk).  Per
+        CTA the parked piece goes first and the piece that waits for parked partials goes last."""
+        lib = _lib.load()
+        nt = C.c_int64(0)
+        check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), 0, 0, None, None, C.byref(nt)))
+        if nt.value == 0:
+            return False
+        tl = np.zeros((nt.value, 4), dtype=np.int32)
+        check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), 0, nt.value, np_ptr(tl), None, C.byref(nt)))
+        fixed = float(os.environ.get("TOR10_SK_FIXED", "3"))          # measured on C3a: (3, 2) 110.9 us,
+        min_piece = int(os.environ.get("TOR10_SK_MINPIECE", "2"))     # (2, 4) 111.5, (4, 4) 113.2, (2, 8) 120.1
+        kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
+        if int(kts.sum()) < 16 * nslots:
+            return False          # too little work per CTA to be worth cutting tiles (plain LPT slots instead)
+        w = kts + fixed
+        share = float(w.sum()) / nslots
+        per_cta = [[] for _ in range(nslots)]      # entries (tile, kt0, kt1)
+        pos = 0.0
+        for ti in range(len(tl)):
+            kt = int(kts[ti])
+            lo, hi = pos, pos + float(w[ti])
+            pos = hi
+            c0 = min(nslots - 1, int(lo / share + 1e-9))
+            c1 = min(nslots - 1, int((hi - 1e-9) / share))
+            if c0 == c1 or kt < 2 * min_piece:
+                per_cta[min(nslots - 1, int((0.5 * (lo + hi)) / share))].append((ti, 0, kt))
+                continue
+            cuts = [0]
+            for c in range(c0 + 1, c1 + 1):        # k-step at which CTA c takes over
+                cuts.append(max(cuts[-1], min(kt, int(round(c * share - lo - fixed)))))
+            cuts.append(kt)
+            merged = []
+            for c, a_, b_ in ((c0 + j, cuts[j], cuts[j + 1]) for j in range(c1 - c0 + 1)):
+                if b_ - a_ < min_piece and merged:
+                    merged[-1] = (merged[-1][0], merged[-1][1], b_)
+                else:
+                    if merged and merged[-1][2] - merged[-1][1] < min_piece:
+                        a_ = merged.pop()[1]
+                    merged.append((c, a_, b_))
+            if len(merged) > 255:
+                return False
+            for c, a_, b_ in merged:
+                per_cta[c].append((ti, a_, b_))
+        holders = {}
+        for c in range(nslots):
+            for ti, a_, b_ in per_cta[c]:
+                holders.setdefault(ti, []).append(c)
+        tiles, pcs, starts = [], [], [0]
+        for c in range(nslots):
+            parked = [x for x in per_cta[c] if x[2] < int(kts[x[0]])]
+            rest = [x for x in per_cta[c] if x[2] >= int(kts[x[0]])]
+            if len(parked) > 1:
+                return False                       # cannot happen with contiguous shares
+            for ti, a_, b_ in parked + [x for x in rest if x[1] == 0] + [x for x in rest if x[1] > 0]:
+                tiles.append(tl[ti])
+                if b_ < int(kts[ti]):
+                    pcs.append((a_, b_, c, 0))
+                elif a_ > 0:
+                    hs = holders[ti]
+                    nfix = len(hs) - 1
+                    if hs != list(range(hs[0], hs[0] + nfix + 1)) or hs[-1] != c:
+                        return False
+                    pcs.append((a_, b_, -1, nfix | (hs[0] << 8)))
+                else:
+                    pcs.append((0, b_, -1, 0))
+            starts.append(len(tiles))
+        dev = self.d_prob.device
+        self.sk_nslots, self.sk_npieces = nslots, len(tiles)
+        self.d_sk_tiles = torch.from_numpy(np.ascontiguousarray(np.array(tiles, dtype=np.int32).reshape(-1, 4))).to(dev)
+        self.d_sk_pieces = torch.from_numpy(np.array(pcs, dtype=np.int32).reshape(-1, 4)).to(dev)
+        self.d_sk_slots = torch.from_numpy(np.array(starts, dtype=np.int32)).to(dev)
+        self.d_sk_ws = torch.empty(nslots * 128 * 34, dtype=torch.float64, device=dev)
+        self.d_sk_flags = torch.zeros(nslots + 1, dtype=torch.int32, device=dev)
+        self.sk_epoch = 0
+        self.sk_parked = sum(1 for x in pcs if x[2] >= 0)
+        return True
+
+    def run_streamk(self, A, B, Cc):
+        self.sk_epoch = self.sk_epoch % 2000000000 + 1
+        check(_lib.load().t10_ggemm_streamk(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), self.nprob,
+                                            self.d_prob.data_ptr(), self.sk_npieces, self.d_sk_tiles.data_ptr(),
+                                            self.d_sk_pieces.data_ptr(), self.sk_nslots, self.d_sk_slots.data_ptr(),
+                                            self.d_sk_ws.data_ptr(), self.d_sk_flags.data_ptr(), self.sk_epoch,
+                                            _lib.stream_ptr()))
 
     def fusable(self):
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
@@ -468,6 +569,8 @@ class GemmGroup:
                                               _lib.stream_ptr()))
 
     def run(self, A, B, Cc):
+        if self.streamk:
+            return self.run_streamk(A, B, Cc)
         check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
                                     self.nprob, self.d_prob.data_ptr(), self.ntiles, self.d_tiles.data_ptr(),
                                     self.nslots, self.d_slots.data_ptr() if self.nslots else None,

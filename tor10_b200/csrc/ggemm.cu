@@ -468,12 +468,14 @@ k_ggemm_f64(const double* __restrict__ Abase, const double* __restrict__ Bbase,
 // even operand offsets; other groups run k_ggemm_f64.
 // One tile (m0, n0) of problem p through the software-pipelined main loop; `smem` = this CTA's dynamic shared
 // memory, `cs_off` = offset (doubles) of the staging tile of the fused all-gather behind the pipeline stages.
-template <class Cfg>
+template <class Cfg, bool SK = false>
 __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const double* __restrict__ Bbase,
                                         double* __restrict__ Cbase, const t10_gemm_problem& p, const int m0,
                                         const int n0, const int m_lim, const int n_lim, const int64_t t,
                                         double* smem, const int cs_off, unsigned long long* __restrict__ trace,
-                                        const PeerOut& peers) {
+                                        const PeerOut& peers, const int4 piece = make_int4(0, 0, -1, 0),
+                                        double* __restrict__ sk_ws = nullptr, int* __restrict__ sk_flags = nullptr,
+                                        const int sk_epoch = 0) {
   static_assert(Cfg::BK == 16, "four k-groups per stage");
   double* As = smem;
   double* Bs = smem + Cfg::STAGES * Cfg::A_STAGE;
@@ -494,6 +496,11 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
   const int m_end = m0 + m_rem, n_end = n0 + n_rem;
   const int KT = (p.k + Cfg::BK - 1) / Cfg::BK;
   const bool active = (m_rem > wm0) && (n_rem > wn0);
+  // Stream-K (SK): this call covers k-steps [kb, ke) of the tile.  A piece without the tile's last k-step parks
+  // its accumulators in workspace slot `pslot` (= this CTA) and raises that slot's flag; the piece with the last
+  // k-step adds the `nfix` parked slots ffix, ffix+1, ... in that order (fixed summation order) and stores.
+  const int kb = SK ? piece.x : 0, ke = SK ? piece.y : KT;
+  const int pslot = SK ? piece.z : -1, nfix = SK ? (piece.w & 0xff) : 0, ffix = SK ? (piece.w >> 8) : 0;
   if (trace != nullptr && threadIdx.x == 0) {   // profiling aid (t10_ggemm_set_trace)
     unsigned smid;
     unsigned long long now;
@@ -541,7 +548,7 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
   __syncthreads();  // previous tile's stages free
 #pragma unroll
   for (int s2 = 0; s2 < Cfg::STAGES - 1; ++s2) {
-    if (s2 < KT) issue(s2, 0, NPASS);
+    if (kb + s2 < ke) issue(kb + s2, 0, NPASS);
     cp_async_commit();
   }
   cp_async_wait<Cfg::STAGES - 2>();
@@ -556,15 +563,15 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
 #pragma unroll
     for (int j = 0; j < Cfg::NI; ++j) bf[buf][j] = bs[j * 8];
   };
-  if (KT > 0) load_frags(0, 0, 0);
+  if (ke > kb) load_frags(kb, 0, 0);
 
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int kt = kb; kt < ke; ++kt) {
     const int nk = kt + Cfg::STAGES - 1;
 #pragma unroll
     for (int grp = 0; grp < 4; ++grp) {
       if (grp < 3) load_frags(kt, grp + 1, (grp + 1) & 1);
-      else if (kt + 1 < KT) load_frags(kt + 1, 0, 0);
-      if (grp < 3 && nk < KT) issue(nk, grp * NPASS / 3, (grp + 1) * NPASS / 3);
+      else if (kt + 1 < ke) load_frags(kt + 1, 0, 0);
+      if (grp < 3 && nk < ke) issue(nk, grp * NPASS / 3, (grp + 1) * NPASS / 3);
       if (grp == 2) {
         cp_async_commit();
         cp_async_wait<Cfg::STAGES - 2>();
@@ -585,6 +592,48 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     trace[4 * t + 3] = now;
+  }
+  if (SK && pslot >= 0) {   // park the partial accumulators, publish, done with this piece
+    if (active) {
+      double2* w = reinterpret_cast<double2*>(sk_ws + (int64_t)pslot * (128 * 34)) + threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+        for (int j = 0; j < Cfg::NI; ++j) w[(i * Cfg::NI + j) * Cfg::THREADS] = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sk_flags + pslot), "r"(sk_epoch) : "memory");
+    }
+    return;
+  }
+  if (SK && nfix > 0) {
+    if (threadIdx.x == 0) {
+      for (int f = 0; f < nfix; ++f) {
+        int v = sk_epoch - 1;
+        for (int spin = 0; spin < (1 << 22); ++spin) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sk_flags + ffix + f) : "memory");
+          if (v == sk_epoch) break;
+          __nanosleep(64);
+        }
+        if (v != sk_epoch) sk_flags[gridDim.x] = 1;   // a parked partial never arrived (reported by the host)
+      }
+    }
+    __syncthreads();
+    if (active) {
+      for (int f = 0; f < nfix; ++f) {
+        const double2* w = reinterpret_cast<const double2*>(sk_ws + (int64_t)(ffix + f) * (128 * 34)) + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; ++i)
+#pragma unroll
+          for (int j = 0; j < Cfg::NI; ++j) {
+            const double2 v = __ldcg(w + (i * Cfg::NI + j) * Cfg::THREADS);
+            acc[i][j][0] += v.x;
+            acc[i][j][1] += v.y;
+          }
+      }
+    }
   }
   if (peers.n > 0) {
     // Fused all-gather: registers -> a dedicated shared tile -> one TMA bulk copy (cp.async.bulk, shared ->
@@ -759,6 +808,35 @@ k_ggemm_f64_mixed(const double* __restrict__ Abase, const double* __restrict__ B
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[q]), "l"(peers.step) : "memory");
       }
     }
+  }
+}
+
+// Stream-K form of the mixed-shape kernel: the table lists PIECES of tiles (k-step ranges); every CTA gets the same
+// number of k-steps, so all of them finish together whatever the tile weights are.  See t10_ggemm_streamk.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS)
+k_ggemm_f64_mixed_sk(const double* __restrict__ Abase, const double* __restrict__ Bbase,
+                     double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
+                     const int4* __restrict__ tiles, const int4* __restrict__ pieces,
+                     const int32_t* __restrict__ slot_start, double* __restrict__ sk_ws, int* __restrict__ sk_flags,
+                     int sk_epoch, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(16) double smem[];
+  const PeerOut nopeers{};
+  const int64_t t_beg = slot_start[blockIdx.x], t_end = slot_start[blockIdx.x + 1];
+  for (int64_t t = t_beg; t < t_end; ++t) {
+    const int4 tile = tiles[t];
+    const int4 pc = pieces[t];
+    const t10_gemm_problem p = prob[tile.x];
+    const int shape = tile.w & 3, m_lim = (tile.w >> 8) & 0xfff, n_lim = (tile.w >> 20) & 0xfff;
+    if (shape == 1)
+      v5_tile<MixRow, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
+                            nopeers, pc, sk_ws, sk_flags, sk_epoch);
+    else if (shape == 2)
+      v5_tile<MixCol, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
+                            nopeers, pc, sk_ws, sk_flags, sk_epoch);
+    else
+      v5_tile<MixSq, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
+                           nopeers, pc, sk_ws, sk_flags, sk_epoch);
   }
 }
 
@@ -1231,6 +1309,34 @@ extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_
   }
   return dispatch_f64(tile_cfg, true, nullptr, (const double*)d_A, (const double*)d_B, (double*)h_peer_C[0], d_prob,
                       ntiles, d_tiles, nslots, d_slot_start, d_sched, (cudaStream_t)stream, po);
+}
+
+extern "C" int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob,
+                                 const t10_gemm_problem* d_prob, int64_t npieces, const int32_t* d_tiles,
+                                 const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
+                                 void* d_ws, int32_t* d_flags, int32_t epoch, t10_stream_t stream) {
+  if (npieces == 0 || nprob == 0) return T10_OK;
+  T10_REQUIRE(npieces > 0 && nprob > 0 && nslots >= 1, T10_ERR_INVALID, "ggemm_streamk: bad counts");
+  T10_REQUIRE(d_pieces && d_tiles && d_slot_start && d_ws && d_flags, T10_ERR_INVALID, "ggemm_streamk: missing table");
+  T10_REQUIRE(((uintptr_t)d_A & 15) == 0 && ((uintptr_t)d_B & 15) == 0, T10_ERR_INVALID,
+              "ggemm_streamk: operand base pointers must be 16-byte aligned");
+  auto kern = k_ggemm_f64_mixed_sk<2>;
+  static int resident = 0;
+  if (resident == 0) {
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_BYTES));
+    int occ = 0;
+    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, MIX_SMEM_BYTES));
+    T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
+    resident = occ * sm_count();
+  }
+  // a waiting piece spins on flags raised by other CTAs of the same launch: all of them must be co-resident
+  T10_REQUIRE(nslots <= resident, T10_ERR_INVALID, "ggemm_streamk: %lld slots but only %d resident CTAs",
+              (long long)nslots, resident);
+  kern<<<(unsigned)nslots, 128, MIX_SMEM_BYTES, (cudaStream_t)stream>>>(
+      (const double*)d_A, (const double*)d_B, (double*)d_C, d_prob, (const int4*)d_tiles, (const int4*)d_pieces,
+      d_slot_start, (double*)d_ws, d_flags, epoch, g_trace);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
 }
 
 extern "C" int t10_ggemm_set_trace(void* d_trace) {
