@@ -460,15 +460,19 @@ def main():
         "fp32_contract": fp32_info,
         "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
                                           + 1 + ((1 if plan._transport in ("fused", "p2p") else 0) if world > 1 else 0))),
-        "roofline": {"kernel": ("k_ggemm_f64_v5 (grouped DMMA GEMM, aligned software-pipelined kernel)"
+        "roofline": {"kernel": ("k_ggemm_f64_mixed_sk (grouped DMMA GEMM, mixed tile shapes, stream-K)"
+                                if getattr(plan.gemm, "streamk", False) else
+                                "k_ggemm_f64_mixed (grouped DMMA GEMM, mixed tile shapes)" if plan.gemm.tile_cfg == 46 else
+                                "k_ggemm_f64_v5 (grouped DMMA GEMM, aligned software-pipelined kernel)"
                                 if plan.gemm.tile_cfg in (40, 42) else "k_ggemm_f64 (grouped DMMA GEMM)"),
                      "bound": "tensor", "achieved": gemm_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf if peak_tf else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                      # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 49.97 MB + 4.21 MB (tile_cfg 40),
                      # 50.00 MB + 3.02 MB (tile_cfg 3)
-                     "traffic": ({40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg) if (world == 1 and args.chi == 4096)
-                                 else None),
+                     # 50.74 MB + 11.09 MB (tile_cfg 46 as stream-K: the parked partial tiles add ~8 MB)
+                     "traffic": ({46: 61.82e6, 40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg)
+                                 if (world == 1 and args.chi == 4096) else None),
                      "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
                      "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
                                     "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "

@@ -362,8 +362,8 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
       40  same tile on the software-pipelined aligned-only kernel, 2 CTAs/SM: 33 TF against 30.6 TF in steady
           state, C3a GEMM stage 123.9 us -- taken when every operand row is 16-byte aligned AS STORED (an
           extra copy of an operand just to align it costs more than it gains);
-      42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned single GEMMs of at least four waves
-          of such tiles (large dense GEMMs);
+      42  64x128 tiles on the same kernel (33.9 TF steady state) for aligned groups of at least four waves of
+          such tiles (large dense GEMMs, the HBM-bound small-K sectors of C5);
       46  the same main loop with mixed tile shapes (64x64 + 32x128 / 128x32 edge strips) for aligned GROUPS
           (block-sparse contractions), run as stream-K when every CTA gets at least 16 k-steps (C3a GEMM stage
           114.7 -> 110.9 us);
@@ -383,10 +383,10 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
         return 3
     if sharded:
         return 40      # with the fused all-gather's staging tile the mixed kernel would drop to one CTA per SM
+    if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
+        return 42      # many waves of work: the larger tile wins (C5, K <= 64 per sector: 30.7 ms against 38.2 ms)
     if len(problems) > 1:
         return 46
-    if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
-        return 42
     return 40
 
 
