@@ -477,8 +477,13 @@ class GemmGroup:
             return False
         tl = np.zeros((nt.value, 4), dtype=np.int32)
         check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), 0, nt.value, np_ptr(tl), None, C.byref(nt)))
-        fixed = float(os.environ.get("TOR10_SK_FIXED", "3"))          # measured on C3a: (3, 2) 110.9 us,
-        min_piece = int(os.environ.get("TOR10_SK_MINPIECE", "2"))     # (2, 4) 111.5, (4, 4) 113.2, (2, 8) 120.1
+        fixed = float(os.environ.get("TOR10_SK_FIXED", "2"))          # measured on C3a: (2, 2) 109.9 us, (3, 2) 110.9,
+        min_piece = int(os.environ.get("TOR10_SK_MINPIECE", "2"))     # (2, 1) 109.7, (2, 4) 111.5, (5, 2) 111.9, (2, 8) 120.1
+        if os.environ.get("TOR10_SK_ORDER", "cost") == "spread":
+            # low-discrepancy interleaving of the cost-sorted list: every CTA's share then mixes long and short
+            # tiles (the short ones carry more pipeline-fill overhead than the model charges)
+            key = (np.arange(len(tl)) * 0.6180339887498949) % 1.0
+            tl = tl[np.argsort(key, kind="stable")]
         kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
         if int(kts.sum()) < 16 * nslots:
             return False          # too little work per CTA to be worth cutting tiles (plain LPT slots instead)
