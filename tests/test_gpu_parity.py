@@ -340,6 +340,28 @@ def test_dense_contract_split_k(T, shape):
     assert rel_err(got.cpu().numpy(), want) <= TOL64
 
 
+@pytest.mark.parametrize("chi", [640, 1000])
+def test_contract_stream_k_forced(T, chi, monkeypatch):
+    """Stream-K forced on small groups: shares of a few k-steps, so tiles are cut into MANY pieces (several parked
+    partials per tile, added in slot order).  Same result as the oracle within 1e-12 and bit-reproducible."""
+    monkeypatch.setenv("TOR10_GGEMM_CFG", "46")
+    monkeypatch.setenv("TOR10_GGEMM_STREAMK", "force")
+    T._plan.clear_caches()
+    A, B = _c3_spec(chi, -3, 3, 1.5)
+    a, b = psym(T, A, seed=21, device=DEV), psym(T, B, seed=22, device=DEV)
+    c1 = T.Contract(a, b)
+    plan = T._plan.get_contract_plan(a, b)
+    assert plan.gemm.tile_cfg == 46 and plan.gemm.streamk and plan.gemm.sk_parked > 0
+    c2 = T.Contract(a, b)
+    oc = orc.contract_sym(osym(A, seed=21), osym(B, seed=22))
+    for x, y, ref in zip(blocks_np(c1), blocks_np(c2), oc.blocks):
+        assert np.array_equal(x, y)
+        assert rel_err(x, ref) <= TOL64
+    if DEV == "cuda":
+        assert int(plan.gemm.d_sk_flags[-1].item()) == 0, "a parked partial never arrived"
+    T._plan.clear_caches()
+
+
 def test_contract_plan_is_cached_and_repeatable(T):
     A, B = _c3_spec(64, -4, 3, 1.5)
     a, b = psym(T, A, seed=11, device=DEV), psym(T, B, seed=12, device=DEV)

@@ -457,7 +457,7 @@ class GemmGroup:
             torch.zeros(48, dtype=torch.uint8, device=device)
         self.streamk = False
         if (dtype == torch.float64 and self.tile_cfg == 46 and not sharded and self.ntiles > 0
-                and os.environ.get("TOR10_GGEMM_STREAMK", "1") == "1"):
+                and os.environ.get("TOR10_GGEMM_STREAMK", "1") in ("1", "force")):
             self.streamk = self.build_streamk(int(ns.value))
         self.flops = float(sum(2.0 * int(p["m"]) * int(p["n"]) * int(p["k"]) for p in self.problems))
         self.bytes = float(sum(int(p["m"]) * int(p["k"]) + int(p["k"]) * int(p["n"]) + int(p["m"]) * int(p["n"])
@@ -485,7 +485,7 @@ class GemmGroup:
             key = (np.arange(len(tl)) * 0.6180339887498949) % 1.0
             tl = tl[np.argsort(key, kind="stable")]
         kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
-        if int(kts.sum()) < 16 * nslots:
+        if int(kts.sum()) < 16 * nslots and os.environ.get("TOR10_GGEMM_STREAMK") != "force":
             return False          # too little work per CTA to be worth cutting tiles (plain LPT slots instead)
         w = kts + fixed
         share = float(w.sum()) / nslots
@@ -547,16 +547,19 @@ class GemmGroup:
         self.d_sk_ws = torch.empty(nslots * 128 * 34, dtype=torch.float64, device=dev)
         self.d_sk_flags = torch.zeros(nslots + 1, dtype=torch.int32, device=dev)
         self.sk_epoch = 0
+        self._sk_static = None
         self.sk_parked = sum(1 for x in pcs if x[2] >= 0)
         return True
 
     def run_streamk(self, A, B, Cc):
         self.sk_epoch = self.sk_epoch % 2000000000 + 1
-        check(_lib.load().t10_ggemm_streamk(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), self.nprob,
-                                            self.d_prob.data_ptr(), self.sk_npieces, self.d_sk_tiles.data_ptr(),
-                                            self.d_sk_pieces.data_ptr(), self.sk_nslots, self.d_sk_slots.data_ptr(),
-                                            self.d_sk_ws.data_ptr(), self.d_sk_flags.data_ptr(), self.sk_epoch,
-                                            _lib.stream_ptr()))
+        st = self._sk_static
+        if st is None:       # pointers of the plan's own tables never change: resolve them once
+            st = self._sk_static = (_lib.load().t10_ggemm_streamk, self.d_prob.data_ptr(), self.d_sk_tiles.data_ptr(),
+                                    self.d_sk_pieces.data_ptr(), self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(),
+                                    self.d_sk_flags.data_ptr())
+        check(st[0](A.data_ptr(), B.data_ptr(), Cc.data_ptr(), self.nprob, st[1], self.sk_npieces, st[2], st[3],
+                    self.sk_nslots, st[4], st[5], st[6], self.sk_epoch, _lib.stream_ptr()))
 
     def fusable(self):
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
@@ -698,14 +701,18 @@ class ContractPlan:
         with _lib.on_device(a.device):
             A = a._arena_tensor()
             B = b._arena_tensor()
-            if self.rel_a is not None:
-                A = self.rel_a.run(A, torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt))
-            if self.rel_b is not None:
-                B = self.rel_b.run(B, torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt))
             sharded = self.shard is not None and self.shard[1] > 1
             fused = sharded and self._transport == "fused" and self.gemm.fusable()
             need_zero = (not self.all_matched) or (self.shard is not None and self._transport == "none")
+            # every buffer is allocated before the first launch, so that the GEMM launch follows the ~10 us
+            # relayout kernel without host work in between
+            Ap = torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt) if self.rel_a is not None else None
+            Bp = torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt) if self.rel_b is not None else None
             Cc = self.Lo.new_arena(dt, zero=need_zero and not fused)   # fused: overwritten by the copy-out
+            if self.rel_a is not None:
+                A = self.rel_a.run(A, Ap)
+            if self.rel_b is not None:
+                B = self.rel_b.run(B, Bp)
             if sharded:
                 from . import parallel
                 if self._transport in ("fused", "p2p") and self._stage is None:
