@@ -225,6 +225,17 @@ int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob
                       const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
                       void* d_ws, int32_t* d_flags, int32_t epoch, t10_stream_t stream);
 
+/* t10_ggemm_streamk with the fused all-gather of t10_ggemm_allgather: every finished tile (the piece that holds
+ * its last k-step, after the fix-up) is staged in shared memory -- the staging tile aliases the pipeline stages,
+ * so two CTAs stay resident per SM -- and pushed to the npeers arenas by TMA bulk copies; the last CTA raises
+ * the peers' flags to `step`.  Arguments as in the two functions it combines.                              */
+int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
+                                void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
+                                int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
+                                const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
+                                const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch,
+                                t10_stream_t stream);
+
 /* Deterministic second half of a split-K product: d_out[i] = sum_{s < nslices} d_ws[s * n + i], added in slice
  * order.  A GEMM whose output is a handful of tiles but whose K is long (the norms and expectation values of
  * iTEBD.py: [1 x 4096] x [4096 x 1]) is issued as `nslices` problems of one t10_ggemm launch, each writing its

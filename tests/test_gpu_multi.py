@@ -60,14 +60,54 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_contract_two_gpus():
+def _worker_streamk(rank, world, port, q):
+    """Stream-K pieces + fused all-gather in one kernel (t10_ggemm_streamk_allgather), forced on a group small
+    enough for a test: tiles are cut across CTAs, parked partials are fixed up, the finished tiles are pushed to
+    both ranks from the staging tile that aliases the pipeline stages."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_GGEMM_CFG="46",
+                      TOR10_GGEMM_STREAMK="force")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import tor10_b200 as T
+    from tor10_b200 import parallel
+    from helpers import psym
+    from test_gpu_parity import _c3_spec
+    A, B = _c3_spec(1000, -7, 6, 2.5)
+    a, b = psym(T, A, seed=51, device="cuda:%d" % rank), psym(T, B, seed=52, device="cuda:%d" % rank)
+    single = T.Contract(a, b)
+    same, err, first, parked = True, 0.0, None, 0
+    for transport in ("fused", "nccl", "fused"):
+        parallel.enable(transport=transport)
+        T._plan.clear_caches()
+        for _ in range(3):
+            sharded = T.Contract(a, b)
+            if first is None:
+                first = [x.clone() for x in sharded.Storage]
+            same = same and all(torch.equal(x, y) for x, y in zip(first, sharded.Storage))
+            err = max(err, max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(single.Storage, sharded.Storage)))
+        g = T._plan.get_contract_plan(a, b).gemm
+        same = same and g.streamk and g.tile_cfg == 46
+        parked = max(parked, g.sk_parked)
+        if transport == "fused":
+            same = same and not parallel.fused_status(T._plan.get_contract_plan(a, b)._stage)
+        parallel.disable()
+        T._plan.clear_caches()
+    same = same and parked > 0
+    torch.cuda.synchronize()
+    q.put((rank, same, err))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_worker, _worker_streamk], ids=["transports", "streamk_allgather"])
+def test_sharded_contract_two_gpus(worker):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
@@ -76,4 +116,4 @@ def test_sharded_contract_two_gpus():
         assert p.exitcode == 0
     for rank, same, err in res:
         assert same, "rank %d: transports disagree, or sharded result differs from the single-GPU result" % rank
-        assert err <= 1e-12
+        assert err <= 1e-12      # against the oracle (transports) / the single-GPU stream-K result (streamk_allgather)

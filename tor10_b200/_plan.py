@@ -375,14 +375,20 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
     if problems is None or not len(problems):
         return 3
     m, n = problems["m"].astype(np.int64), problems["n"].astype(np.int64)
-    if sharded and int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count():
-        return 8
     aligned = base_aligned and bool(((problems["lda"] % 2 == 0) & (problems["ldb"] % 2 == 0)
                                      & (problems["a_off"] % 2 == 0) & (problems["b_off"] % 2 == 0)).all())
+    few = sharded and int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count()
+    if few and not (aligned and os.environ.get("TOR10_SHARDED_SK", "0") == "1"):
+        return 8
     if not aligned:
         return 3
     if sharded:
-        return 40      # with the fused all-gather's staging tile the mixed kernel would drop to one CTA per SM
+        # a rank's share of the sectors: stream-K on the mixed-shape kernel when every CTA still gets 16 k-steps
+        # (its all-gather staging tile aliases the pipeline stages, so two CTAs stay resident), else plain 64x64
+        ksteps = int((((m + 63) // 64) * ((n + 63) // 64) * ((problems["k"].astype(np.int64) + 15) // 16)).sum())
+        if os.environ.get("TOR10_SHARDED_SK", "0") == "1" and ksteps >= 16 * 2 * _sm_count():
+            return 46
+        return 8 if few else 40
     if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
         return 42      # many waves of work: the larger tile wins (C5, K <= 64 per sector: 30.7 ms against 38.2 ms)
     if len(problems) > 1:
@@ -409,6 +415,7 @@ class GemmGroup:
         self.problems = np.ascontiguousarray(problems, dtype=_lib.GEMM_PROBLEM_DTYPE)
         self.nprob = len(self.problems)
         self.dtype_code = _lib.dtype_code(dtype)
+        auto_cfg = tile_cfg is None and os.environ.get("TOR10_GGEMM_CFG") is None
         if tile_cfg is None:
             if dtype == torch.float64:
                 with torch.cuda.device(device):
@@ -456,9 +463,15 @@ class GemmGroup:
         self.d_prob = torch.from_numpy(self.problems.view(np.uint8).reshape(-1)).to(device) if self.nprob else \
             torch.zeros(48, dtype=torch.uint8, device=device)
         self.streamk = False
-        if (dtype == torch.float64 and self.tile_cfg == 46 and not sharded and self.ntiles > 0
+        if (dtype == torch.float64 and self.tile_cfg == 46 and self.ntiles > 0
                 and os.environ.get("TOR10_GGEMM_STREAMK", "1") in ("1", "force")):
             self.streamk = self.build_streamk(int(ns.value))
+        if sharded and auto_cfg and self.tile_cfg == 46 and not self.streamk:
+            # too little work to cut tiles after all: the plain 64x64 (or 32x32) kernels
+            few = int((((pr["m"].astype(np.int64) + 63) // 64) * ((pr["n"].astype(np.int64) + 63) // 64)).sum()) \
+                < 1.5 * _sm_count()
+            return self.__init__(problems, device, dtype, tile_cfg=8 if few else 40, base_aligned=base_aligned,
+                                 sharded=sharded)
         self.flops = float(sum(2.0 * int(p["m"]) * int(p["n"]) * int(p["k"]) for p in self.problems))
         self.bytes = float(sum(int(p["m"]) * int(p["k"]) + int(p["k"]) * int(p["n"]) + int(p["m"]) * int(p["n"])
                                for p in self.problems))
@@ -568,6 +581,14 @@ class GemmGroup:
     def run_allgather(self, A, B, peer_ptrs, flag_ptrs, step, done_ctr):
         """peer_ptrs / flag_ptrs: ctypes (c_void_p * n) of every rank's arena base / of this rank's flag slot
         on every rank (this rank's own included)."""
+        if self.streamk:
+            self.sk_epoch = self.sk_epoch % 2000000000 + 1
+            check(_lib.load().t10_ggemm_streamk_allgather(
+                A.data_ptr(), B.data_ptr(), len(peer_ptrs), peer_ptrs, flag_ptrs, step, done_ctr.data_ptr(),
+                self.nprob, self.d_prob.data_ptr(), self.sk_npieces, self.d_sk_tiles.data_ptr(),
+                self.d_sk_pieces.data_ptr(), self.sk_nslots, self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(),
+                self.d_sk_flags.data_ptr(), self.sk_epoch, _lib.stream_ptr()))
+            return
         check(_lib.load().t10_ggemm_allgather(self.tile_cfg, A.data_ptr(), B.data_ptr(), len(peer_ptrs), peer_ptrs,
                                               flag_ptrs, step, done_ctr.data_ptr(),
                                               self.nprob, self.d_prob.data_ptr(), self.ntiles,

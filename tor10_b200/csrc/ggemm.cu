@@ -545,6 +545,9 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
     }
   };
 
+  // cs_off < 0: the staging tile of the fused all-gather aliases the pipeline stages (keeps two CTAs per SM for
+  // the mixed-shape kernels); the previous tile's bulk copies must then have read it before new loads land
+  if (cs_off < 0 && peers.n > 0 && warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncthreads();  // previous tile's stages free
 #pragma unroll
   for (int s2 = 0; s2 < Cfg::STAGES - 1; ++s2) {
@@ -640,9 +643,9 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
     // global) per tile row and rank, issued by warp 0 and left in flight while the CTA computes its next
     // tile.  The copy engine streams whole 512-byte rows over NVLink; no LSU stores, no registers.
     constexpr int CLD = Cfg::BN + 2;
-    double* Cs = smem + cs_off;
-    if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left Cs
-    __syncthreads();
+    double* Cs = smem + (cs_off < 0 ? 0 : cs_off);
+    if (cs_off >= 0 && warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile has left Cs
+    __syncthreads();   // (alias mode: every warp is done reading the last stage)
     if (active) {
 #pragma unroll
       for (int i = 0; i < Cfg::MI; ++i)
@@ -761,7 +764,7 @@ constexpr int MIX_SMEM_BYTES = MIX_STAGE_DOUBLES * 8;
 static_assert(MixSq::STAGES * (MixSq::A_STAGE + MixSq::B_STAGE) <= MIX_STAGE_DOUBLES, "");
 static_assert(MixRow::STAGES * (MixRow::A_STAGE + MixRow::B_STAGE) <= MIX_STAGE_DOUBLES, "");
 static_assert(MixCol::STAGES * (MixCol::A_STAGE + MixCol::B_STAGE) <= MIX_STAGE_DOUBLES, "");
-static_assert(64 * 66 <= MIX_CS_DOUBLES && 32 * 130 <= MIX_CS_DOUBLES, "");
+static_assert(64 * 66 <= MIX_CS_DOUBLES && 32 * 130 <= MIX_CS_DOUBLES && MIX_CS_DOUBLES <= MIX_STAGE_DOUBLES, "");
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS)
@@ -783,11 +786,11 @@ k_ggemm_f64_mixed(const double* __restrict__ Abase, const double* __restrict__ B
     // tile.w = shape | valid rows << 8 | valid columns << 20 (0 = up to the sector edge)
     const int shape = tile.w & 3, m_lim = (tile.w >> 8) & 0xfff, n_lim = (tile.w >> 20) & 0xfff;
     if (shape == 1)
-      v5_tile<MixRow>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace, peers);
+      v5_tile<MixRow>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers);
     else if (shape == 2)
-      v5_tile<MixCol>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace, peers);
+      v5_tile<MixCol>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers);
     else
-      v5_tile<MixSq>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace, peers);
+      v5_tile<MixSq>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers);
   };
   for (int64_t t = t_beg; t < t_end; t += t_step) run_tile(t);
   if (peers.n > 0) {   // the bulk copies still in flight must have landed before this rank signals
@@ -819,9 +822,9 @@ k_ggemm_f64_mixed_sk(const double* __restrict__ Abase, const double* __restrict_
                      double* __restrict__ Cbase, const t10_gemm_problem* __restrict__ prob,
                      const int4* __restrict__ tiles, const int4* __restrict__ pieces,
                      const int32_t* __restrict__ slot_start, double* __restrict__ sk_ws, int* __restrict__ sk_flags,
-                     int sk_epoch, unsigned long long* __restrict__ trace) {
+                     int sk_epoch, unsigned long long* __restrict__ trace, const __grid_constant__ PeerOut peers) {
   extern __shared__ __align__(16) double smem[];
-  const PeerOut nopeers{};
+  const int warp = threadIdx.x >> 5;
   const int64_t t_beg = slot_start[blockIdx.x], t_end = slot_start[blockIdx.x + 1];
   for (int64_t t = t_beg; t < t_end; ++t) {
     const int4 tile = tiles[t];
@@ -829,14 +832,34 @@ k_ggemm_f64_mixed_sk(const double* __restrict__ Abase, const double* __restrict_
     const t10_gemm_problem p = prob[tile.x];
     const int shape = tile.w & 3, m_lim = (tile.w >> 8) & 0xfff, n_lim = (tile.w >> 20) & 0xfff;
     if (shape == 1)
-      v5_tile<MixRow, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
-                            nopeers, pc, sk_ws, sk_flags, sk_epoch);
+      v5_tile<MixRow, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers, pc, sk_ws,
+                            sk_flags, sk_epoch);
     else if (shape == 2)
-      v5_tile<MixCol, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
-                            nopeers, pc, sk_ws, sk_flags, sk_epoch);
+      v5_tile<MixCol, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers, pc, sk_ws,
+                            sk_flags, sk_epoch);
     else
-      v5_tile<MixSq, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, MIX_STAGE_DOUBLES, trace,
-                           nopeers, pc, sk_ws, sk_flags, sk_epoch);
+      v5_tile<MixSq, true>(Abase, Bbase, Cbase, p, tile.y, tile.z, m_lim, n_lim, t, smem, -1, trace, peers, pc, sk_ws,
+                           sk_flags, sk_epoch);
+  }
+
+  if (peers.n > 0) {   // the bulk copies still in flight must have landed before this rank signals
+    if (warp == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+  }
+  if (peers.n > 0 && peers.done_ctr != nullptr) {
+    __syncthreads();   // every thread's tile stores precede thread 0's fence
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(peers.done_ctr, 1) == (int)gridDim.x - 1) {
+        *peers.done_ctr = 0;
+        __threadfence_system();
+        for (int q = 0; q < peers.n; ++q)
+          if (peers.flag[q] != nullptr)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[q]), "l"(peers.step) : "memory");
+      }
+    }
   }
 }
 
@@ -1056,10 +1079,9 @@ static int launch_f64_mixed(bool launch, int* nslots_out, const double* A, const
                             const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
                             const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64_mixed<2>;
-  constexpr int SMEM_ALL = MIX_SMEM_BYTES + MIX_CS_DOUBLES * 8;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALL));
+    T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_BYTES));
     int occ = 0;
     T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, MIX_SMEM_BYTES));
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "ggemm kernel does not fit on an SM");
@@ -1078,8 +1100,8 @@ static int launch_f64_mixed(bool launch, int* nslots_out, const double* A, const
   } else {
     grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count() * ctas_per_sm);
   }
-  kern<<<grid, 128, peers.n > 0 ? SMEM_ALL : MIX_SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start,
-                                                                  g_trace, peers);
+  // the all-gather's staging tile aliases the pipeline stages (v5_tile, cs_off < 0): same footprint either way
+  kern<<<grid, 128, MIX_SMEM_BYTES, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, slot_start, g_trace, peers);
   T10_LAUNCH_CHECK();
   return T10_OK;
 }
@@ -1311,11 +1333,10 @@ extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_
                       ntiles, d_tiles, nslots, d_slot_start, d_sched, (cudaStream_t)stream, po);
 }
 
-extern "C" int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob,
-                                 const t10_gemm_problem* d_prob, int64_t npieces, const int32_t* d_tiles,
-                                 const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
-                                 void* d_ws, int32_t* d_flags, int32_t epoch, t10_stream_t stream) {
-  if (npieces == 0 || nprob == 0) return T10_OK;
+static int launch_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob, const t10_gemm_problem* d_prob,
+                          int64_t npieces, const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
+                          const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch,
+                          const PeerOut& po, cudaStream_t stream) {
   T10_REQUIRE(npieces > 0 && nprob > 0 && nslots >= 1, T10_ERR_INVALID, "ggemm_streamk: bad counts");
   T10_REQUIRE(d_pieces && d_tiles && d_slot_start && d_ws && d_flags, T10_ERR_INVALID, "ggemm_streamk: missing table");
   T10_REQUIRE(((uintptr_t)d_A & 15) == 0 && ((uintptr_t)d_B & 15) == 0, T10_ERR_INVALID,
@@ -1332,11 +1353,52 @@ extern "C" int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, in
   // a waiting piece spins on flags raised by other CTAs of the same launch: all of them must be co-resident
   T10_REQUIRE(nslots <= resident, T10_ERR_INVALID, "ggemm_streamk: %lld slots but only %d resident CTAs",
               (long long)nslots, resident);
-  kern<<<(unsigned)nslots, 128, MIX_SMEM_BYTES, (cudaStream_t)stream>>>(
+  kern<<<(unsigned)nslots, 128, MIX_SMEM_BYTES, stream>>>(
       (const double*)d_A, (const double*)d_B, (double*)d_C, d_prob, (const int4*)d_tiles, (const int4*)d_pieces,
-      d_slot_start, (double*)d_ws, d_flags, epoch, g_trace);
+      d_slot_start, (double*)d_ws, d_flags, epoch, g_trace, po);
   T10_LAUNCH_CHECK();
   return T10_OK;
+}
+
+extern "C" int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob,
+                                 const t10_gemm_problem* d_prob, int64_t npieces, const int32_t* d_tiles,
+                                 const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
+                                 void* d_ws, int32_t* d_flags, int32_t epoch, t10_stream_t stream) {
+  if (npieces == 0 || nprob == 0) return T10_OK;
+  PeerOut po;
+  memset(&po, 0, sizeof(po));
+  return launch_streamk(d_A, d_B, d_C, nprob, d_prob, npieces, d_tiles, d_pieces, nslots, d_slot_start, d_ws, d_flags,
+                        epoch, po, (cudaStream_t)stream);
+}
+
+extern "C" int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
+                                           void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
+                                           int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
+                                           const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
+                                           const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch,
+                                           t10_stream_t stream) {
+  T10_REQUIRE(npeers >= 1 && npeers <= T10_MAX_PEERS, T10_ERR_INVALID, "ggemm_streamk_allgather: 1..%d arenas",
+              T10_MAX_PEERS);
+  T10_REQUIRE(npieces >= 0 && nprob >= 0, T10_ERR_INVALID, "negative counts");
+  T10_REQUIRE(h_peer_flag == nullptr || d_done_ctr != nullptr, T10_ERR_INVALID, "flags need an arrival counter");
+  PeerOut po;
+  memset(&po, 0, sizeof(po));
+  po.n = npeers;
+  po.step = step;
+  po.done_ctr = d_done_ctr;
+  for (int i = 0; i < npeers; ++i) {
+    po.ptr[i] = (double*)h_peer_C[i];
+    po.flag[i] = h_peer_flag ? (unsigned long long*)h_peer_flag[i] : nullptr;
+  }
+  if (npieces == 0 || nprob == 0) {
+    if (h_peer_flag) {
+      k_raise_flags<<<1, 32, 0, (cudaStream_t)stream>>>(po);
+      T10_LAUNCH_CHECK();
+    }
+    return T10_OK;
+  }
+  return launch_streamk(d_A, d_B, h_peer_C[0], nprob, d_prob, npieces, d_tiles, d_pieces, nslots, d_slot_start, d_ws,
+                        d_flags, epoch, po, (cudaStream_t)stream);
 }
 
 extern "C" int t10_ggemm_set_trace(void* d_trace) {
