@@ -56,7 +56,7 @@ def _worker(rank, world, port, q):
         parallel.disable()
         T._plan.clear_caches()
     torch.cuda.synchronize()
-    q.put((rank, same, err))
+    q.put((rank, "" if same else "transports disagree, or sharded result differs from the single-GPU result", err))
     dist.destroy_process_group()
 
 
@@ -76,26 +76,33 @@ def _worker_streamk(rank, world, port, q):
     A, B = _c3_spec(1000, -7, 6, 2.5)
     a, b = psym(T, A, seed=51, device="cuda:%d" % rank), psym(T, B, seed=52, device="cuda:%d" % rank)
     single = T.Contract(a, b)
-    same, err, first, parked = True, 0.0, None, 0
+    # the k-cuts of a tile depend on the rank's share of the sectors, which differs between the transports (LPT
+    # owners for the fused path, contiguous ranges for NCCL): bit-identical within a transport, rounding-level
+    # agreement (1e-13) with the single-GPU stream-K result across them
+    why, err, parked = [], 0.0, 0
     for transport in ("fused", "nccl", "fused"):
         parallel.enable(transport=transport)
         T._plan.clear_caches()
+        first = None
         for _ in range(3):
             sharded = T.Contract(a, b)
             if first is None:
                 first = [x.clone() for x in sharded.Storage]
-            same = same and all(torch.equal(x, y) for x, y in zip(first, sharded.Storage))
+            if not all(torch.equal(x, y) for x, y in zip(first, sharded.Storage)):
+                why.append("%s: not bit-reproducible" % transport)
             err = max(err, max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(single.Storage, sharded.Storage)))
-        g = T._plan.get_contract_plan(a, b).gemm
-        same = same and g.streamk and g.tile_cfg == 46
-        parked = max(parked, g.sk_parked)
-        if transport == "fused":
-            same = same and not parallel.fused_status(T._plan.get_contract_plan(a, b)._stage)
+        pl = T._plan.get_contract_plan(a, b)
+        if not (pl.gemm.streamk and pl.gemm.tile_cfg == 46):
+            why.append("%s: stream-K not in use (cfg %d)" % (transport, pl.gemm.tile_cfg))
+        parked = max(parked, getattr(pl.gemm, "sk_parked", 0))
+        if transport == "fused" and parallel.fused_status(pl._stage):
+            why.append("fused: a wait on a peer's flag timed out")
         parallel.disable()
         T._plan.clear_caches()
-    same = same and parked > 0
+    if parked == 0:
+        why.append("no tile was cut across CTAs")
     torch.cuda.synchronize()
-    q.put((rank, same, err))
+    q.put((rank, "; ".join(why), err))
     dist.destroy_process_group()
 
 
@@ -114,6 +121,6 @@ def test_sharded_contract_two_gpus(worker):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, same, err in res:
-        assert same, "rank %d: transports disagree, or sharded result differs from the single-GPU result" % rank
+    for rank, why, err in res:
+        assert not why, "rank %d: %s" % (rank, why)
         assert err <= 1e-12      # against the oracle (transports) / the single-GPU stream-K result (streamk_allgather)

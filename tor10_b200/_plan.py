@@ -378,7 +378,7 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
     aligned = base_aligned and bool(((problems["lda"] % 2 == 0) & (problems["ldb"] % 2 == 0)
                                      & (problems["a_off"] % 2 == 0) & (problems["b_off"] % 2 == 0)).all())
     few = sharded and int((((m + 63) // 64) * ((n + 63) // 64)).sum()) < 1.5 * _sm_count()
-    if few and not (aligned and os.environ.get("TOR10_SHARDED_SK", "0") == "1"):
+    if few and not (aligned and os.environ.get("TOR10_SHARDED_SK", "1") == "1"):
         return 8
     if not aligned:
         return 3
@@ -386,7 +386,7 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
         # a rank's share of the sectors: stream-K on the mixed-shape kernel when every CTA still gets 16 k-steps
         # (its all-gather staging tile aliases the pipeline stages, so two CTAs stay resident), else plain 64x64
         ksteps = int((((m + 63) // 64) * ((n + 63) // 64) * ((problems["k"].astype(np.int64) + 15) // 16)).sum())
-        if os.environ.get("TOR10_SHARDED_SK", "0") == "1" and ksteps >= 16 * 2 * _sm_count():
+        if os.environ.get("TOR10_SHARDED_SK", "1") == "1" and ksteps >= 16 * 2 * _sm_count():
             return 46
         return 8 if few else 40
     if int((((m + 63) // 64) * ((n + 127) // 128)).sum()) >= 8 * _sm_count():
