@@ -358,7 +358,7 @@ def test_contract_stream_k_forced(T, chi, monkeypatch):
         assert np.array_equal(x, y)
         assert rel_err(x, ref) <= TOL64
     if DEV == "cuda":
-        assert int(plan.gemm.d_sk_flags[-1].item()) == 0, "a parked partial never arrived"
+        assert int(plan.gemm.d_sk_flags[plan.gemm.sk_nslots].item()) == 0, "a parked partial never arrived"
     T._plan.clear_caches()
 
 

@@ -69,6 +69,74 @@ def test_tile_planner_host_side(T):
         assert lib.t10_ggemm_tile_shape(cfg, ctypes.byref(b0), ctypes.byref(b1)) == 0 and (b0.value, b1.value) == (bm, bn)
 
 
+def _streamk_tables(T, prob, nslots, phases, monkeypatch):
+    """GemmGroup.build_streamk is host code (numpy + the host-side tile planner): run it without a device."""
+    monkeypatch.setenv("TOR10_GGEMM_STREAMK", "force")
+    g = T._plan.GemmGroup.__new__(T._plan.GemmGroup)
+    g.problems, g.nprob = prob, len(prob)
+    g.d_prob = torch.zeros(48, dtype=torch.uint8)
+    assert g.build_streamk(nslots, phases=phases)
+    return g, g.d_sk_tiles.numpy(), g.d_sk_pieces.numpy(), g.d_sk_slots.numpy()
+
+
+@pytest.mark.parametrize("phases", [1, 2, 3])
+@pytest.mark.parametrize("nslots", [7, 40, 296])
+def test_streamk_piece_tables(T, nslots, phases, monkeypatch):
+    """The stream-K schedule (one or several phases): every tile's k-steps are covered exactly once, a parked
+    piece owns its park slot, the finishing piece lists exactly its tile's parked slots in k order, and running the
+    CTAs' lists in order never deadlocks (a waiting piece only waits for pieces that can run before it)."""
+    rng = np.random.default_rng(nslots * 10 + phases)
+    prob = np.zeros(9, dtype=T._lib.GEMM_PROBLEM_DTYPE)
+    for i in range(len(prob)):
+        m, n, k = int(rng.integers(20, 400)), int(rng.integers(20, 400)), int(rng.integers(16, 1500))
+        prob[i] = (0, 0, 0, m, n, k, k + (k & 1), n + (n & 1), n + (n & 1))
+    g, tiles, pcs, starts = _streamk_tables(T, prob, nslots, phases, monkeypatch)
+    assert starts[0] == 0 and starts[-1] == len(tiles) == len(pcs) and len(starts) == nslots + 1
+    kts = (prob["k"][tiles[:, 0]].astype(np.int64) + 15) // 16
+    by_tile = {}
+    for t in range(len(tiles)):
+        by_tile.setdefault(tuple(tiles[t]), []).append((int(pcs[t, 0]), int(pcs[t, 1]), int(pcs[t, 2]), int(pcs[t, 3]), int(kts[t])))
+    # the planner's own tile list, each tile exactly once
+    n = ctypes.c_int64(0)
+    lib = T._lib.load()
+    assert lib.t10_ggemm_plan_tiles(46, len(prob), T._lib.np_ptr(prob), 0, 0, None, None, ctypes.byref(n)) == 0
+    assert len(by_tile) == n.value
+    slots_seen = set()
+    for key, ps in by_tile.items():
+        ps.sort()
+        assert ps[0][0] == 0 and ps[-1][1] == ps[-1][4]
+        assert all(a[1] == b[0] for a, b in zip(ps, ps[1:])), "k ranges must tile [0, KT) without gaps or overlap"
+        assert all(a[1] > a[0] for a in ps)
+        parked = [a[2] for a in ps[:-1]]
+        assert all(x >= 0 and x != nslots for x in parked) and ps[-1][2] == -1
+        assert not (set(parked) & slots_seen)
+        slots_seen |= set(parked)
+        nfix, first = ps[-1][3] & 0xff, ps[-1][3] >> 8
+        assert nfix == len(parked) and parked == list(range(first, first + nfix))
+    assert g.sk_parked == len(slots_seen) and max(slots_seen, default=0) < len(g.d_sk_flags)
+    assert (max(slots_seen, default=0) + 1) * 128 * 34 <= g.d_sk_ws.numel()
+    # execution: CTAs advance through their lists; a finishing piece needs its parked slots raised
+    pc = starts[:-1].astype(np.int64).copy()
+    raised, progress = set(), True
+    while progress:
+        progress = False
+        for c in range(nslots):
+            while pc[c] < starts[c + 1]:
+                a, b, slot, w = (int(x) for x in pcs[pc[c]])
+                need = set(range(w >> 8, (w >> 8) + (w & 0xff)))
+                if slot < 0 and not need <= raised:
+                    break
+                if slot >= 0:
+                    raised.add(slot)
+                pc[c] += 1
+                progress = True
+    assert (pc == starts[1:]).all(), "the schedule deadlocks"
+    # equal shares: no CTA holds much more than the mean
+    load = np.array([sum(int(pcs[t, 1] - pcs[t, 0]) + 2 for t in range(starts[c], starts[c + 1])) for c in range(nslots)])
+    if load.mean() >= 16 * g.sk_phases:
+        assert load.max() <= 1.25 * load.mean() + 4 * g.sk_phases
+
+
 def test_no_cpu_compute_path(T):
     if torch.cuda.is_available():
         pytest.skip("CUDA present")

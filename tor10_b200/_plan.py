@@ -465,7 +465,10 @@ class GemmGroup:
         self.streamk = False
         if (dtype == torch.float64 and self.tile_cfg == 46 and self.ntiles > 0
                 and os.environ.get("TOR10_GGEMM_STREAMK", "1") in ("1", "force")):
-            self.streamk = self.build_streamk(int(ns.value))
+            # a sharded rank pushes its tiles to the peers as they finish: two groups of tiles, so that half of them
+            # finish (and travel) while the other half computes
+            self.streamk = self.build_streamk(int(ns.value), phases=int(os.environ.get("TOR10_SK_PHASES", "1"))
+                                              if sharded else 1)
         if sharded and auto_cfg and self.tile_cfg == 46 and not self.streamk:
             # too little work to cut tiles after all: the plain 64x64 (or 32x32) kernels
             few = int((((pr["m"].astype(np.int64) + 63) // 64) * ((pr["n"].astype(np.int64) + 63) // 64)).sum()) \
@@ -477,7 +480,7 @@ class GemmGroup:
                                for p in self.problems))
 
     # ---- stream-K on the mixed-shape kernel: balance k-steps, not tiles -------------------------------------
-    def build_streamk(self, nslots):
+    def build_streamk(self, nslots, phases=1):
         """Cut the tile list (t10_ggemm_plan_tiles, cfg 46, heaviest first) into `nslots` equal shares of k-steps
         (a k-step of the aligned kernel costs the same whatever the tile's raggedness; +2 per piece for the
         pipeline fill).  A tile cut across CTAs becomes pieces: the CTAs holding its leading k-ranges park partial
@@ -500,68 +503,85 @@ class GemmGroup:
         kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
         if int(kts.sum()) < 16 * nslots and os.environ.get("TOR10_GGEMM_STREAMK") != "force":
             return False          # too little work per CTA to be worth cutting tiles (plain LPT slots instead)
-        w = kts + fixed
-        share = float(w.sum()) / nslots
-        per_cta = [[] for _ in range(nslots)]      # entries (tile, kt0, kt1)
-        pos = 0.0
-        for ti in range(len(tl)):
-            kt = int(kts[ti])
-            lo, hi = pos, pos + float(w[ti])
-            pos = hi
-            c0 = min(nslots - 1, int(lo / share + 1e-9))
-            c1 = min(nslots - 1, int((hi - 1e-9) / share))
-            if c0 == c1 or kt < 2 * min_piece:
-                per_cta[min(nslots - 1, int((0.5 * (lo + hi)) / share))].append((ti, 0, kt))
-                continue
-            cuts = [0]
-            for c in range(c0 + 1, c1 + 1):        # k-step at which CTA c takes over
-                cuts.append(max(cuts[-1], min(kt, int(round(c * share - lo - fixed)))))
-            cuts.append(kt)
-            merged = []
-            for c, a_, b_ in ((c0 + j, cuts[j], cuts[j + 1]) for j in range(c1 - c0 + 1)):
-                if b_ - a_ < min_piece and merged:
-                    merged[-1] = (merged[-1][0], merged[-1][1], b_)
-                else:
-                    if merged and merged[-1][2] - merged[-1][1] < min_piece:
-                        a_ = merged.pop()[1]
-                    merged.append((c, a_, b_))
-            if len(merged) > 255:
-                return False
-            for c, a_, b_ in merged:
-                per_cta[c].append((ti, a_, b_))
-        holders = {}
+        # PHASES (sharded ranks with the fused all-gather): the tiles are dealt into `phases` groups of equal work and
+        # every group is cut into nslots shares of its own, run one group after the other.  With one group all CTAs
+        # finish their last tile at the same moment and most of the result is pushed to the peers in the kernel's
+        # last microseconds; with G groups (G - 1) / G of it is pushed while the next group computes.
+        phases = max(1, int(phases))
+        while phases > 1 and int(kts.sum()) < 8 * phases * nslots:
+            phases -= 1
+        tiles, pcs = [[] for _ in range(nslots)], [[] for _ in range(nslots)]
+        nparked = 0
+        for g in range(phases):
+            sel = np.arange(g, len(tl), phases)          # every phases-th tile of the cost-sorted list
+            w = kts[sel] + fixed
+            share = float(w.sum()) / nslots
+            per_cta = [[] for _ in range(nslots)]      # entries (tile, kt0, kt1)
+            pos = 0.0
+            for j, ti in enumerate(sel):
+                kt = int(kts[ti])
+                lo, hi = pos, pos + float(w[j])
+                pos = hi
+                c0 = min(nslots - 1, int(lo / share + 1e-9))
+                c1 = min(nslots - 1, int((hi - 1e-9) / share))
+                if c0 == c1 or kt < 2 * min_piece:
+                    per_cta[min(nslots - 1, int((0.5 * (lo + hi)) / share))].append((ti, 0, kt))
+                    continue
+                cuts = [0]
+                for c in range(c0 + 1, c1 + 1):        # k-step at which CTA c takes over
+                    cuts.append(max(cuts[-1], min(kt, int(round(c * share - lo - fixed)))))
+                cuts.append(kt)
+                merged = []
+                for c, a_, b_ in ((c0 + i, cuts[i], cuts[i + 1]) for i in range(c1 - c0 + 1)):
+                    if b_ - a_ < min_piece and merged:
+                        merged[-1] = (merged[-1][0], merged[-1][1], b_)
+                    else:
+                        if merged and merged[-1][2] - merged[-1][1] < min_piece:
+                            a_ = merged.pop()[1]
+                        merged.append((c, a_, b_))
+                if len(merged) > 255:
+                    return False
+                for c, a_, b_ in merged:
+                    per_cta[c].append((ti, a_, b_))
+            holders = {}
+            for c in range(nslots):
+                for ti, a_, b_ in per_cta[c]:
+                    holders.setdefault(ti, []).append(c)
+            slot0 = g * (nslots + 1)                   # park slots of this phase (flag nslots reports errors)
+            for c in range(nslots):
+                parked = [x for x in per_cta[c] if x[2] < int(kts[x[0]])]
+                rest = [x for x in per_cta[c] if x[2] >= int(kts[x[0]])]
+                if len(parked) > 1:
+                    return False                       # cannot happen with contiguous shares
+                nparked += len(parked)
+                for ti, a_, b_ in parked + [x for x in rest if x[1] == 0] + [x for x in rest if x[1] > 0]:
+                    tiles[c].append(tl[ti])
+                    if b_ < int(kts[ti]):
+                        pcs[c].append((a_, b_, slot0 + c, 0))
+                    elif a_ > 0:
+                        hs = holders[ti]
+                        nfix = len(hs) - 1
+                        if hs != list(range(hs[0], hs[0] + nfix + 1)) or hs[-1] != c:
+                            return False
+                        pcs[c].append((a_, b_, -1, nfix | ((slot0 + hs[0]) << 8)))
+                    else:
+                        pcs[c].append((0, b_, -1, 0))
+        starts = [0]
         for c in range(nslots):
-            for ti, a_, b_ in per_cta[c]:
-                holders.setdefault(ti, []).append(c)
-        tiles, pcs, starts = [], [], [0]
-        for c in range(nslots):
-            parked = [x for x in per_cta[c] if x[2] < int(kts[x[0]])]
-            rest = [x for x in per_cta[c] if x[2] >= int(kts[x[0]])]
-            if len(parked) > 1:
-                return False                       # cannot happen with contiguous shares
-            for ti, a_, b_ in parked + [x for x in rest if x[1] == 0] + [x for x in rest if x[1] > 0]:
-                tiles.append(tl[ti])
-                if b_ < int(kts[ti]):
-                    pcs.append((a_, b_, c, 0))
-                elif a_ > 0:
-                    hs = holders[ti]
-                    nfix = len(hs) - 1
-                    if hs != list(range(hs[0], hs[0] + nfix + 1)) or hs[-1] != c:
-                        return False
-                    pcs.append((a_, b_, -1, nfix | (hs[0] << 8)))
-                else:
-                    pcs.append((0, b_, -1, 0))
-            starts.append(len(tiles))
+            starts.append(starts[-1] + len(tiles[c]))
+        tiles = [x for c in range(nslots) for x in tiles[c]]
+        pcs = [x for c in range(nslots) for x in pcs[c]]
+        self.sk_phases = phases
         dev = self.d_prob.device
         self.sk_nslots, self.sk_npieces = nslots, len(tiles)
         self.d_sk_tiles = torch.from_numpy(np.ascontiguousarray(np.array(tiles, dtype=np.int32).reshape(-1, 4))).to(dev)
         self.d_sk_pieces = torch.from_numpy(np.array(pcs, dtype=np.int32).reshape(-1, 4)).to(dev)
         self.d_sk_slots = torch.from_numpy(np.array(starts, dtype=np.int32)).to(dev)
-        self.d_sk_ws = torch.empty(nslots * 128 * 34, dtype=torch.float64, device=dev)
-        self.d_sk_flags = torch.zeros(nslots + 1, dtype=torch.int32, device=dev)
+        self.d_sk_ws = torch.empty(phases * (nslots + 1) * 128 * 34, dtype=torch.float64, device=dev)
+        self.d_sk_flags = torch.zeros(phases * (nslots + 1), dtype=torch.int32, device=dev)
         self.sk_epoch = 0
         self._sk_static = None
-        self.sk_parked = sum(1 for x in pcs if x[2] >= 0)
+        self.sk_parked = nparked
         return True
 
     def run_streamk(self, A, B, Cc):
