@@ -229,8 +229,8 @@ int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob
  * its last k-step, after the fix-up) is staged in shared memory -- the staging tile aliases the pipeline stages,
  * so two CTAs stay resident per SM -- and pushed to the npeers arenas by TMA bulk copies; the last CTA raises
  * the peers' flags to `step`.  Arguments as in the two functions it combines.                              */
-int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
-                                void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
+int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, int self_index,
+                                void* const* h_peer_C, void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
                                 int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
                                 const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
                                 const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch,
@@ -249,10 +249,12 @@ int t10_reduce_slices(int dtype, const void* d_ws, void* d_out, int64_t n, int n
  * remaining tiles' math.  With h_peer_flag != NULL the last CTA to finish raises *h_peer_flag[q] (this
  * rank's uint64 slot in rank q's flag array, peer-mapped) to `step` with system-scope release semantics;
  * d_done_ctr is a zero-initialised int32 owned by the caller (reset by the kernel).
+ * self_index: which of the arenas lives in THIS GPU's memory (-1: unknown); the aligned kernels (40, 42, 46,
+ * stream-K) write that one with plain vector stores and only the others through the copy engine.
  * t10_wait_copy is the consumer: it waits until d_flags[0..nflags) >= step, then copies n elements
  * d_src -> d_dst (staging arena -> result arena).  *d_err is set if a flag does not arrive in ~2 s.      */
-int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
-                        void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
+int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers, int self_index,
+                        void* const* h_peer_C, void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
                         int64_t nprob, const t10_gemm_problem* d_prob, int64_t ntiles,
                         const int32_t* d_tiles, int64_t nslots, const int32_t* d_slot_start,
                         int32_t* d_sched, t10_stream_t stream);

@@ -60,7 +60,7 @@ def run(transport, iters=30):
             ptrs = (C.c_void_p * st.world)(*st.peer_ptrs[k])
             fptrs = (C.c_void_p * st.world)(*st.peer_flag_ptrs[k])
             st.steps[k] += 1
-            pl.gemm.run_allgather(Aa, Bb, ptrs, fptrs, st.steps[k], st.done_ctr)
+            pl.gemm.run_allgather(Aa, Bb, ptrs, fptrs, st.steps[k], st.done_ctr, self_index=st.rank)
             e[4].record()
             e[5].record()
             n = Cc.numel() // 4 * 4

@@ -48,7 +48,10 @@ def launch(variant):
     else:    # "self": the same epilogue, one destination: this rank's own staging arena
         ptrs = (C.c_void_p * 1)(st.peer_ptrs[k][rank]); fl = (C.c_void_p * 1)(st.peer_flag_ptrs[k][rank])
     st.steps[k] += 1
-    g.run_allgather(Aa, Bb, ptrs, fl, st.steps[k], st.done_ctr)
+    # TOR10_TRACE_SELF_BULK=1: the local arena through the copy engine too (how r01_trace_fused_n2.json was taken)
+    bulk_self = os.environ.get("TOR10_TRACE_SELF_BULK") == "1"
+    g.run_allgather(Aa, Bb, ptrs, fl, st.steps[k], st.done_ctr,
+                    self_index=-1 if bulk_self else (rank if variant == "fused" else 0))
 
 
 out = {}

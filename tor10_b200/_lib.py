@@ -72,10 +72,10 @@ SIGNATURES = {
     "t10_ggemm_tf32_status": [_p],
     "t10_ggemm_set_trace": [_p],
     "t10_ggemm_streamk": [_p, _p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _p],
-    "t10_ggemm_streamk_allgather": [_p, _p, _i, _p, _p, C.c_uint64, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _p],
+    "t10_ggemm_streamk_allgather": [_p, _p, _i, _i, _p, _p, C.c_uint64, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _p],
     "t10_reduce_slices": [_i, _p, _p, _l, _i, _p],
     "t10_relayout_runs": [_i, _p, _p, _l, _p, _l, _p, _p],
-    "t10_ggemm_allgather": [_i, _p, _p, _i, _p, _p, C.c_uint64, _p, _l, _p, _l, _p, _l, _p, _p, _p],
+    "t10_ggemm_allgather": [_i, _p, _p, _i, _i, _p, _p, C.c_uint64, _p, _l, _p, _l, _p, _l, _p, _p, _p],
     "t10_wait_copy": [_i, _p, _p, _l, _p, _i, C.c_uint64, _p, _p],
     "t10_probe_f64_peak": [_i, _i, _p, _p],
     "t10_probe_f64_occupancy": [_i, _i, _p, _p],

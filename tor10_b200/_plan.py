@@ -598,19 +598,19 @@ class GemmGroup:
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
         return self.dtype_code == _lib.dtype_code(torch.float64) and self.tile_cfg in FUSABLE_CFGS
 
-    def run_allgather(self, A, B, peer_ptrs, flag_ptrs, step, done_ctr):
+    def run_allgather(self, A, B, peer_ptrs, flag_ptrs, step, done_ctr, self_index=-1):
         """peer_ptrs / flag_ptrs: ctypes (c_void_p * n) of every rank's arena base / of this rank's flag slot
-        on every rank (this rank's own included)."""
+        on every rank (this rank's own included, at position self_index)."""
         if self.streamk:
             self.sk_epoch = self.sk_epoch % 2000000000 + 1
             check(_lib.load().t10_ggemm_streamk_allgather(
-                A.data_ptr(), B.data_ptr(), len(peer_ptrs), peer_ptrs, flag_ptrs, step, done_ctr.data_ptr(),
+                A.data_ptr(), B.data_ptr(), len(peer_ptrs), self_index, peer_ptrs, flag_ptrs, step, done_ctr.data_ptr(),
                 self.nprob, self.d_prob.data_ptr(), self.sk_npieces, self.d_sk_tiles.data_ptr(),
                 self.d_sk_pieces.data_ptr(), self.sk_nslots, self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(),
                 self.d_sk_flags.data_ptr(), self.sk_epoch, _lib.stream_ptr()))
             return
-        check(_lib.load().t10_ggemm_allgather(self.tile_cfg, A.data_ptr(), B.data_ptr(), len(peer_ptrs), peer_ptrs,
-                                              flag_ptrs, step, done_ctr.data_ptr(),
+        check(_lib.load().t10_ggemm_allgather(self.tile_cfg, A.data_ptr(), B.data_ptr(), len(peer_ptrs), self_index,
+                                              peer_ptrs, flag_ptrs, step, done_ctr.data_ptr(),
                                               self.nprob, self.d_prob.data_ptr(), self.ntiles,
                                               self.d_tiles.data_ptr(), self.nslots,
                                               self.d_slots.data_ptr() if self.nslots else None,

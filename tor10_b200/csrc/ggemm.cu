@@ -151,6 +151,8 @@ struct LeanLoader {
 constexpr int T10_MAX_PEERS = 8;
 struct PeerOut {
   int n;
+  int self;                                  // index of the destination in THIS GPU's memory, or -1 (v5 kernels:
+                                             // written by plain vector stores, the others by bulk copies)
   double* ptr[T10_MAX_PEERS];
   unsigned long long* flag[T10_MAX_PEERS];   // this rank's slot in rank q's flag array (NULL: no signalling)
   unsigned long long step;
@@ -667,6 +669,7 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
           const unsigned src = (unsigned)__cvta_generic_to_shared(Cs + r * CLD);
 #pragma unroll 1
           for (int q = 0; q < peers.n; ++q) {
+            if (q == peers.self) continue;
             double* o = peers.ptr[q] + off;
             if (bytes)
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o), "r"(src), "r"(bytes)
@@ -675,6 +678,18 @@ __device__ __forceinline__ void v5_tile(const double* __restrict__ Abase, const 
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (peers.self >= 0) {
+        // the local destination: 16-byte stores by all threads (a 512-byte bulk copy costs the SM's copy engine
+        // ~125 ns whatever its destination; 64 of them per tile are slower than the LSU path for local memory)
+        double* o = peers.ptr[peers.self] + p.c_off + (int64_t)m0 * p.ldc + n0;
+        for (int idx = threadIdx.x; idx < rows * (Cfg::BN / 2); idx += Cfg::THREADS) {
+          const int r = idx / (Cfg::BN / 2), c2 = (idx % (Cfg::BN / 2)) * 2;
+          if (c2 + 1 < cols)
+            *reinterpret_cast<double2*>(o + (int64_t)r * p.ldc + c2) = *reinterpret_cast<const double2*>(Cs + r * CLD + c2);
+          else if (c2 < cols)
+            o[(int64_t)r * p.ldc + c2] = Cs[r * CLD + c2];
+        }
       }
     } else {
       for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::THREADS) {
@@ -1305,7 +1320,7 @@ __global__ void k_raise_flags(PeerOut peers) {   // a rank without tiles still h
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flag[threadIdx.x]), "l"(peers.step) : "memory");
 }
 
-extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers,
+extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npeers, int self_index,
                                    void* const* h_peer_C, void* const* h_peer_flag, uint64_t step,
                                    int32_t* d_done_ctr, int64_t nprob, const t10_gemm_problem* d_prob,
                                    int64_t ntiles, const int32_t* d_tiles, int64_t nslots,
@@ -1316,6 +1331,7 @@ extern "C" int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_
   PeerOut po;
   memset(&po, 0, sizeof(po));
   po.n = npeers;
+  po.self = (self_index >= 0 && self_index < npeers) ? self_index : -1;
   po.step = step;
   po.done_ctr = d_done_ctr;
   for (int i = 0; i < npeers; ++i) {
@@ -1367,11 +1383,13 @@ extern "C" int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, in
   if (npieces == 0 || nprob == 0) return T10_OK;
   PeerOut po;
   memset(&po, 0, sizeof(po));
+  po.self = -1;
   return launch_streamk(d_A, d_B, d_C, nprob, d_prob, npieces, d_tiles, d_pieces, nslots, d_slot_start, d_ws, d_flags,
                         epoch, po, (cudaStream_t)stream);
 }
 
-extern "C" int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, void* const* h_peer_C,
+extern "C" int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, int self_index,
+                                           void* const* h_peer_C,
                                            void* const* h_peer_flag, uint64_t step, int32_t* d_done_ctr,
                                            int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
                                            const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
@@ -1384,6 +1402,7 @@ extern "C" int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int
   PeerOut po;
   memset(&po, 0, sizeof(po));
   po.n = npeers;
+  po.self = (self_index >= 0 && self_index < npeers) ? self_index : -1;
   po.step = step;
   po.done_ctr = d_done_ctr;
   for (int i = 0; i < npeers; ++i) {

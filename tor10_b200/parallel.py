@@ -187,7 +187,7 @@ def gemm_allgather(stage, gemm, A, B, arena):
         stage.args[("push", k)] = args
     stage.steps[k] += 1
     step = stage.steps[k]
-    gemm.run_allgather(A, B, args[0], args[1], step, stage.done_ctr)
+    gemm.run_allgather(A, B, args[0], args[1], step, stage.done_ctr, self_index=stage.rank)
     n = arena.numel() // 4 * 4      # whole 16-byte vectors (the arena ends in >= 16 elements of padding)
     _lib.check(_lib.load().t10_wait_copy(_lib.dtype_code(arena.dtype), arena.data_ptr(), stage.bufs[k].data_ptr(),
                                          n, stage.flags[k].data_ptr(), stage.world, step,
