@@ -231,3 +231,39 @@ def test_symmetric_matmul_chain(T):
     dense = T.UniTensor(bonds=[T.Bond(chi), T.Bond(28)], rowrank=1, device=torch.device(DEV))
     with pytest.raises(Exception):
         T.Matmul(a, dense)
+
+
+def test_pickle_and_save_load_round_trip(T, tmp_path):
+    """SURVEY 8b serialisation (UniTensor.py:3449-3502): arena-backed symmetric tensors pickle -- contiguous and
+    permuted (not yet relaid out) -- and come back with the same metadata, blocks and behaviour."""
+    import pickle
+    v = u1z2_leg(24, -3, 3, 1.3)
+    p = [[1, 1], [-1, 1]]
+    A = {"bonds": [bond(24, -1, v), bond(2, -1, p), bond(2, 1, p), bond(24, 1, v)], "rowrank": 2, "labels": [0, 1, 2, 3]}
+    a = psym(T, A, seed=77, device=DEV)
+    b = pickle.loads(pickle.dumps(a))
+    assert b.labels.tolist() == a.labels.tolist() and b.rowrank == a.rowrank and b.is_contiguous()
+    assert np.array_equal(b._block_qnums, a._block_qnums)
+    for x, y in zip(blocks_np(a), blocks_np(b)):
+        assert np.array_equal(x, y)
+    # a permuted tensor keeps its pending permutation through the round trip
+    a.Permute([0, 2, 1, 3], rowrank=2)
+    assert not a.is_contiguous()
+    T.Save(a, str(tmp_path / "perm"))
+    c = T.Load(str(tmp_path / "perm.uniT"))
+    assert not c.is_contiguous() and c.labels.tolist() == a.labels.tolist()
+    for x, y in zip(blocks_np(a.Contiguous()), blocks_np(c.Contiguous())):
+        assert np.array_equal(x, y)
+    # and contracts like the original
+    B = {"bonds": [bond(2, -1, p), bond(24, -1, v), bond(2, 1, p), bond(24, 1, v)], "rowrank": 2, "labels": [2, 3, 4, 5]}
+    t2 = psym(T, B, seed=78, device=DEV)
+    r1, r2 = T.Contract(a, t2), T.Contract(c, t2)
+    for x, y in zip(blocks_np(r1), blocks_np(r2)):
+        assert np.array_equal(x, y)
+    # dense tensors too
+    d = T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], rowrank=1, device=torch.device(DEV))
+    d.Storage = torch.arange(12, dtype=torch.float64).reshape(3, 4).to(DEV)
+    e = pickle.loads(pickle.dumps(d))
+    assert torch.equal(e.Storage.cpu(), d.Storage.cpu())
+    with pytest.raises(Exception):
+        T.Load(str(tmp_path / "missing.uniT"))
