@@ -137,6 +137,37 @@ def test_streamk_piece_tables(T, nslots, phases, monkeypatch):
         assert load.max() <= 1.25 * load.mean() + 4 * g.sk_phases
 
 
+def test_tile_cfg_selection_rules(T, monkeypatch):
+    """_plan.pick_tile_cfg (the kernel chosen for an fp64 group) as a decision table; SM count pinned to 148."""
+    monkeypatch.setattr(T._plan, "_sm_count", lambda: 148)
+    for k in ("TOR10_GGEMM_CFG", "TOR10_SHARDED_SK"):
+        monkeypatch.delenv(k, raising=False)
+
+    def group(shapes, odd=False):
+        pr = np.zeros(len(shapes), dtype=T._lib.GEMM_PROBLEM_DTYPE)
+        for i, (m, n, k) in enumerate(shapes):
+            pr[i] = (0, 0, 0, m, n, k, k + (1 if odd else 0), n, n)
+        return pr
+
+    pick = T._plan.pick_tile_cfg
+    c3a_like = group([(400, 400, 400)] * 40)
+    assert pick(None) == 3 and pick(group([])) == 3
+    assert pick(c3a_like, base_aligned=True) == 46                     # block-sparse group: mixed shapes (+ stream-K)
+    assert pick(c3a_like, base_aligned=False) == 3                     # operand base not 16-byte aligned
+    assert pick(group([(400, 400, 400)] * 40, odd=True), base_aligned=True) == 3   # odd leading dimension
+    assert pick(group([(2048, 2048, 2048)]), base_aligned=True) == 40  # one dense GEMM, few waves
+    assert pick(group([(8192, 8192, 64)] * 4), base_aligned=True) == 42   # many waves of 64x128 tiles
+    # sharded ranks: stream-K while every CTA keeps 16 k-steps, else 64x64, else 32x32 for a handful of tiles
+    assert pick(c3a_like, sharded=True, base_aligned=True) == 46
+    assert pick(group([(400, 400, 32)] * 40), sharded=True, base_aligned=True) == 40
+    assert pick(group([(100, 100, 64)] * 10), sharded=True, base_aligned=True) == 8
+    assert pick(group([(100, 100, 64)] * 10), sharded=True, base_aligned=False) == 8
+    monkeypatch.setenv("TOR10_SHARDED_SK", "0")
+    assert pick(c3a_like, sharded=True, base_aligned=True) == 40
+    monkeypatch.setenv("TOR10_GGEMM_CFG", "2")
+    assert pick(c3a_like, base_aligned=True) == 2
+
+
 def test_no_cpu_compute_path(T):
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
