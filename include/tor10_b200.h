@@ -213,13 +213,14 @@ int t10_ggemm(int dtype, int tile_cfg, const void* d_A, const void* d_B, void* d
 /* Stream-K form of the mixed-shape aligned fp64 kernel (tile_cfg 46).  The table lists PIECES: entry t is k-steps
  * [kt0, kt1) (units of 16) of the tile d_tiles[t] (as produced by t10_ggemm_plan_tiles for cfg 46), described by
  * d_pieces[t] = {kt0, kt1, park_slot, nfix | first_fix << 8}.  A piece with park_slot >= 0 does not contain its
- * tile's last k-step: it writes its partial accumulators to workspace slot park_slot (= its CTA; d_ws holds
- * nslots * 4352 doubles) and raises d_flags[park_slot] to `epoch`.  The piece that contains the last k-step
+ * tile's last k-step: it writes its partial accumulators to workspace slot park_slot (any index other than
+ * nslots, normally its CTA; d_ws holds (largest park_slot + 1) * 4352 doubles, d_flags one more int32 than
+ * that) and raises d_flags[park_slot] to `epoch`.  The piece that contains the last k-step
  * (park_slot = -1) adds the nfix parked slots first_fix, first_fix+1, ... in that order and stores the tile, so
  * the result does not depend on timing.  d_slot_start[nslots+1] delimits each CTA's pieces; the host lists a
  * CTA's parked piece first and its waiting piece last, and nslots must not exceed the resident CTAs
- * (t10_ggemm_slots).  d_flags: int32[nslots + 1], zero-initialised once; `epoch` must differ from launch to
- * launch (a counter); d_flags[nslots] != 0 afterwards reports a parked partial that never arrived.        */
+ * (t10_ggemm_slots).  d_flags: at least int32[nslots + 1], zero-initialised once; `epoch` must differ from
+ * launch to launch (a counter); d_flags[nslots] != 0 afterwards reports a parked partial that never arrived. */
 int t10_ggemm_streamk(const void* d_A, const void* d_B, void* d_C, int64_t nprob,
                       const t10_gemm_problem* d_prob, int64_t npieces, const int32_t* d_tiles,
                       const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
