@@ -184,7 +184,8 @@ def test_no_cpu_compute_path(T):
 
 
 def test_product_never_imports_the_oracle():
-    """oracle/ is test infrastructure: no file of the package (or the example script) may import it."""
+    """oracle/ and tests/abi_emulator.py are test infrastructure: no file of the package (or the example script)
+    may import or mention them."""
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     offenders = []
@@ -193,7 +194,8 @@ def test_product_never_imports_the_oracle():
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
-                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "abi_emulator" in txt \
+                            or "emu_plugin" in txt:
                         offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
 
