@@ -7,13 +7,18 @@ as shipped (compatibility shim of tests/golden/make_golden.py).  Random inputs, 
   dense  Contract with random shared labels, rowranks 0..rank, tagged / untagged, diagonal operands, permuted
          operands, outer products, bra/ket violations (same exception behaviour), Matmul incl. diagonal operands
 
-    python tests/fuzz_vs_reference.py sym   <seed> <cases> [maxdim]
-    python tests/fuzz_vs_reference.py dense <seed> <cases>
+  blocks GetValidQnums / GetBlock / PutBlock on contiguous and permuted (not relaid out) symmetric tensors, then the
+         relayout of the modified tensor (bit-exact outside quirk Q3)
+
+    python tests/fuzz_vs_reference.py sym    <seed> <cases> [maxdim]
+    python tests/fuzz_vs_reference.py dense  <seed> <cases>
+    python tests/fuzz_vs_reference.py blocks <seed> <cases>      (the reference prints "[unphys pos]" lines)
 
 Round-1 campaign (seeds 2..7 x 1500 sym cases with maxdim 7, seeds 2..4 x 5000 dense cases): 0 discrepancies in
 6 133 block maps, 5 622 relayouts (458 of them quirk-Q3 inputs: maps and metadata compared only), 4 558 symmetric
 and 14 589 dense contractions (+ 411 inputs on which both implementations raise), 7 608 contractions of permuted
-operands, 14 554 Matmuls.
+operands, 14 554 Matmuls; blocks, seeds 2..5 x 2000: 9 509 GetBlock + PutBlock pairs.  One deviation found and
+fixed: `_block_qnums` after a Permute that leaves no common sector (empty table in the reference, exception here).
 """
 import os
 import sys
@@ -249,6 +254,105 @@ def fuzz_dense(argv):
     return len(fails)
 
 
+def fuzz_blocks(argv):
+    seed, ncase = int(argv[0]) if len(argv) > 0 else 1, int(argv[1]) if len(argv) > 1 else 300
+    rng = np.random.default_rng(seed)
+    fails, stats = [], {"getblock": 0, "putblock": 0, "q3": 0, "skipped": 0, "raise_both": 0}
+    t0 = time.time()
+    for it in range(ncase):
+        syms = G.SYMSETS[int(rng.integers(0, len(G.SYMSETS)))]
+        spec = G.rand_tensor_spec(rng, syms=syms)
+        try:
+            r = G.fill(G.mk_tensor(spec), 100 + it)
+        except Exception:
+            stats["skipped"] += 1; continue
+        p = psym(T, spec, seed=100 + it, device="cpu")
+        rank = len(spec["bonds"])
+        permuted = rng.random() < 0.7
+        if permuted:
+            perm = [int(x) for x in rng.permutation(rank)]; rr = int(rng.integers(1, rank))
+            if perm == list(range(rank)) and rr != spec["rowrank"]:
+                continue
+            try:
+                r.Permute(perm, rowrank=rr)
+            except Exception:
+                stats["skipped"] += 1; continue
+            try:
+                p.Permute(perm, rowrank=rr)
+            except Exception as e:
+                fails.append(("perm%d" % it, repr(e))); continue
+            o = osym(spec, seed=100 + it); o.permute(perm, rowrank=rr)
+            try:
+                o.clone().contiguous_(vectorised=True); wd = True
+            except AssertionError:
+                wd = False
+            except Exception:
+                wd = False
+            if not wd:
+                stats["q3"] += 1
+        else:
+            wd = True
+        try:
+            rq = np.asarray(r.GetValidQnums())
+        except Exception as e:
+            try:
+                p.GetValidQnums(); fails.append(("gvq%d" % it, "ref raises %r" % (e,)))
+            except Exception:
+                stats["raise_both"] += 1
+            continue
+        pq = np.asarray(p.GetValidQnums())
+        if not np.array_equal(rq, pq):
+            fails.append(("gvq%d" % it, "valid qnums")); continue
+        for q in rq:
+            try:
+                rb = r.GetBlock(*q.tolist())
+            except Exception as e:
+                try:
+                    p.GetBlock(*q.tolist()); fails.append(("get%d" % it, "ref raises %r, product not" % (e,)))
+                except Exception:
+                    stats["raise_both"] += 1
+                continue
+            try:
+                pb = p.GetBlock(*q.tolist())
+            except Exception as e:
+                fails.append(("get%d" % it, "product raises %r" % (e,))); continue
+            stats["getblock"] += 1
+            x, y = rb.Storage.numpy(), pb.Storage.cpu().numpy()
+            if x.shape != y.shape:
+                fails.append(("get%d q%s" % (it, q.tolist()), "shape %s %s" % (x.shape, y.shape))); continue
+            if wd and not np.array_equal(x, y):
+                fails.append(("get%d q%s perm%d" % (it, q.tolist(), permuted), "values"))
+            # PutBlock of a fresh random block, then read back everything
+            newb = rng.random(x.shape)
+            rb.Storage = torch.from_numpy(newb.copy()); pb.Storage = torch.from_numpy(newb.copy())
+            try:
+                r.PutBlock(rb, *q.tolist())
+                rok = True
+            except Exception as e:
+                rok = e
+            try:
+                p.PutBlock(pb, *q.tolist())
+                pok = True
+            except Exception as e:
+                pok = e
+            if (rok is True) != (pok is True):
+                fails.append(("put%d q%s" % (it, q.tolist()), "ref %r / prod %r" % (rok, pok))); continue
+            if rok is True:
+                stats["putblock"] += 1
+        if wd:
+            try:
+                rc = r.Contiguous(); pc = p.Contiguous()
+                for x, y in zip(rc.Storage, pc.Storage):
+                    if not np.array_equal(x.numpy(), y.cpu().numpy()):
+                        fails.append(("after_put%d perm%d" % (it, permuted), "values")); break
+            except Exception as e:
+                fails.append(("after_put%d" % it, repr(e)))
+    print("seed", seed, stats, "fails", len(fails), "time %.1fs" % (time.time() - t0))
+    for f in fails[:20]:
+        print("  FAIL", f)
+    return len(fails)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sym"
-    sys.exit(1 if (fuzz_sym if mode == "sym" else fuzz_dense)(sys.argv[2:]) else 0)
+    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks}[mode](sys.argv[2:]) else 0)

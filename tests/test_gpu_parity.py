@@ -570,3 +570,18 @@ def test_itebd_trajectory_matches_reference(T):
     got = np.array(out["energies"])
     assert got.shape == z["energies"].shape
     assert np.abs(got - z["energies"]).max() <= 1e-9
+
+
+def test_permute_without_common_sector_keeps_an_empty_table(T):
+    """The reference's Permute only recomputes `_block_qnums` (UniTensor.py:2310-2313): when the new row and column
+    spaces share no charge the table is EMPTY and nothing raises until the tensor is relaid out (found by
+    tests/fuzz_vs_reference.py; Z2 with a lone BRA bond in the row space, quirk Q3)."""
+    z2 = [["Zn", 2]]
+    spec = {"bonds": [{"dim": 1, "btype": -1, "qnums": [[1]], "syms": z2}, {"dim": 1, "btype": -1, "qnums": [[0]], "syms": z2},
+                      {"dim": 2, "btype": 1, "qnums": [[1], [0]], "syms": z2}], "rowrank": 2, "labels": [8, 11, 6]}
+    t = psym(T, spec, seed=3, device=DEV)
+    t.Permute([2, 1, 0], rowrank=2)
+    q = t.GetValidQnums()
+    assert np.asarray(q).shape == (0, 1) and np.asarray(t._block_qnums).dtype == np.int64
+    with pytest.raises(TypeError):
+        t.Contiguous()

@@ -268,8 +268,13 @@ class UniTensor:
         if not self.is_symm:
             return None
         if self._bq is None:
-            lay = self._layout if self._layout_current() else self._logical_layout()
-            self._bq = lay.block_qnums
+            try:
+                lay = self._layout if self._layout_current() else self._logical_layout()
+                self._bq = lay.block_qnums
+            except _lib.NoValidBlock:
+                # a Permute whose new row / column spaces share no charge: the reference's Permute leaves an empty
+                # table (UniTensor.py:2310-2313, Bond.py:13-28) and raises only when the tensor is relaid out
+                self._bq = np.zeros((0, self.bonds[0].qnums.shape[1]), dtype=np.int64)
         return self._bq
 
     @_block_qnums.setter
