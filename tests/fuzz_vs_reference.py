@@ -15,6 +15,10 @@ as shipped (compatibility shim of tests/golden/make_golden.py).  Random inputs, 
     python tests/fuzz_vs_reference.py blocks <seed> <cases>      (the reference prints "[unphys pos]" lines)
     python tests/fuzz_vs_reference.py net    <seed> <cases>      random dense networks of 2..5 tensors through
                                                                  Network.Fromfile / Put / Launch, with and without Order
+    python tests/fuzz_vs_reference.py ops    <seed> <cases>      random sequences of Permute (by index / label),
+                                                                 CombineBonds, Reshape, View, SetLabels, SetRowRank,
+                                                                 Contiguous on dense tensors: labels, bonds, rowrank,
+                                                                 contiguity flag and storage after every step
 
 Round-1 campaign (seeds 2..7 x 1500 sym cases with maxdim 7, seeds 2..4 x 5000 dense cases): 0 discrepancies in
 6 133 block maps, 5 622 relayouts (458 of them quirk-Q3 inputs: maps and metadata compared only), 4 558 symmetric
@@ -22,6 +26,11 @@ and 14 589 dense contractions (+ 411 inputs on which both implementations raise)
 operands, 14 554 Matmuls; blocks, seeds 2..5 x 2000: 9 509 GetBlock + PutBlock pairs.  One deviation found and
 fixed: `_block_qnums` after a Permute that leaves no common sector (empty table in the reference, exception here).
 net, seeds 2..4 x 3000: 9 000 launches (4 538 with a random Order), no discrepancy.
+ops, seeds 1..4 x 3000 sequences (26 310 operations): found and fixed -- dense CombineBonds without permute_back sets
+rowrank to 1 / rank-1 (UniTensor.py:4132-4139), View refuses non-contiguous tensors and copies (:2583-2594), Reshape
+keeps torch.reshape's view-or-copy behaviour (contiguity flag).  Left as documented deviations, all reference bugs:
+CombineBonds(by_label=False) and the tagged fuse-to-the-back branch raise NameError there (1 487 sequences), and
+permute_back=True never permutes the storage back (`a.Stoarge = ...`, :4121; 163 sequences, metadata compared).
 """
 import os
 import sys
@@ -436,6 +445,131 @@ def fuzz_net(argv):
     return len(fails)
 
 
+def fuzz_ops(argv):
+    seed, ncase = int(argv[0]) if len(argv) > 0 else 1, int(argv[1]) if len(argv) > 1 else 300
+    rng = np.random.default_rng(seed)
+    fails, stats = [], {"ops": 0, "both_raise": 0, "seqs": 0}
+    t0 = time.time()
+
+    def fused_pos(r, args, prev_labels):
+        """Position of the fused bond after CombineBonds(permute_back=True): where its first constituent was."""
+        X = args[1][0]
+        first = X[0] if args[2].get("by_label", True) else prev_labels[X[0]]
+        lab = args[2].get("new_label", first)
+        return [int(x) for x in r.labels].index(int(lab))
+
+
+    def same(r, p, where):
+        try:
+            if list(r.labels) != list(p.labels) or int(r.rowrank) != int(p.rowrank) or bool(r.is_diag) != bool(p.is_diag):
+                fails.append((where, "meta ref %s rr%s / prod %s rr%s" % (list(r.labels), r.rowrank, list(p.labels), p.rowrank))); return False
+            if [int(b.dim) for b in r.bonds] != [int(b.dim) for b in p.bonds]:
+                fails.append((where, "bond dims %s vs %s" % ([b.dim for b in r.bonds], [b.dim for b in p.bonds]))); return False
+            if [b.bondType for b in r.bonds] != [{T.BD_BRA: ref.BD_BRA, T.BD_KET: ref.BD_KET, T.BD_REG: ref.BD_REG}[b.bondType] for b in p.bonds]:
+                fails.append((where, "bond types")); return False
+            if bool(r.is_contiguous()) != bool(p.is_contiguous()):
+                fails.append((where, "contiguous flag %s vs %s" % (r.is_contiguous(), p.is_contiguous()))); return False
+            x, y = r.Storage.contiguous().numpy(), p.Storage.contiguous().cpu().numpy()
+            if x.shape != y.shape or (x.size and np.abs(x - y).max() > 1e-12 * max(1.0, np.abs(x).max())):
+                fails.append((where, "storage %s vs %s" % (x.shape, y.shape))); return False
+        except Exception as e:
+            fails.append((where, "compare raised %r" % (e,))); return False
+        return True
+
+    for it in range(ncase):
+        rank = int(rng.integers(1, 5))
+        dims = [int(rng.integers(1, 4)) for _ in range(rank)]
+        labels = [int(x) for x in rng.permutation(np.arange(-4, 12))[:rank]]
+        rr = int(rng.integers(0, rank + 1))
+        tagged = rng.random() < 0.3
+        bt = [-1] * rr + [1] * (rank - rr) if tagged else [0] * rank
+        vals = rng.random(tuple(dims))
+        objs = []
+        for lib in (ref, T):
+            BT = {1: lib.BD_BRA, -1: lib.BD_KET, 0: lib.BD_REG}
+            kw = {} if lib is ref else {"device": torch.device("cpu")}
+            t = lib.UniTensor(bonds=[lib.Bond(d, BT[b]) for d, b in zip(dims, bt)], rowrank=rr, labels=labels, **kw)
+            t.Storage = torch.from_numpy(vals.copy())
+            objs.append(t)
+        r, p = objs
+        stats["seqs"] += 1
+        trace = []
+        for step in range(int(rng.integers(1, 6))):
+            n = len(r.labels)
+            kind = rng.choice(["permute", "permute_label", "combine", "reshape", "setlabels", "contiguous", "setrowrank", "view"])
+            if kind == "permute":
+                args = ("Permute", ([int(x) for x in rng.permutation(n)],), {"rowrank": int(rng.integers(0, n + 1))} if rng.random() < 0.7 else {})
+            elif kind == "permute_label":
+                args = ("Permute", ([int(x) for x in rng.permutation(list(r.labels))],), {"by_label": True, **({"rowrank": int(rng.integers(0, n + 1))} if rng.random() < 0.5 else {})})
+            elif kind == "combine":
+                if n < 2: continue
+                k = int(rng.integers(2, n + 1))
+                pick = [int(x) for x in rng.choice(n, size=k, replace=False)]
+                by_label = rng.random() < 0.5
+                X = [int(r.labels[i]) for i in pick] if by_label else pick
+                kw = {"by_label": by_label, "permute_back": bool(rng.random() < 0.5)}
+                if rng.random() < 0.4: kw["new_label"] = 77 + step
+                args = ("CombineBonds", (X,), kw)
+            elif kind in ("reshape", "view"):
+                tot = int(np.prod([b.dim for b in r.bonds]))
+                # random factorisation
+                fac, rem = [], tot
+                for _ in range(int(rng.integers(1, 4))):
+                    ds = [d for d in range(1, rem + 1) if rem % d == 0]
+                    d = int(rng.choice(ds)); fac.append(d); rem //= d
+                fac.append(rem)
+                kw = {}
+                if rng.random() < 0.5: kw["new_labels"] = [int(x) for x in rng.permutation(np.arange(20, 40))[:len(fac)]]
+                args = ("Reshape" if kind == "reshape" else "View", (fac, int(rng.integers(0, len(fac) + 1))), kw)
+            elif kind == "setlabels":
+                args = ("SetLabels", ([int(x) for x in rng.permutation(np.arange(-9, 20))[:n]],), {})
+            elif kind == "setrowrank":
+                args = ("SetRowRank", (int(rng.integers(0, n + 1)),), {})
+            else:
+                args = ("Contiguous", (), {})
+            trace.append(args)
+            prev_labels = [int(x) for x in r.labels]
+            out = []
+            for obj in (r, p):
+                try:
+                    out.append(getattr(obj, args[0])(*args[1], **args[2]))
+                except Exception as e:
+                    out.append(e)
+            er, ep = isinstance(out[0], Exception), isinstance(out[1], Exception)
+            where = "seq%d rank%d dims%s labels%s rr%d tagged%d :: %s" % (it, rank, dims, labels, rr, tagged, trace)
+            if er and isinstance(out[0], NameError):
+                stats["ref_bug"] = stats.get("ref_bug", 0) + 1      # reference bugs: undefined names in CombineBonds
+                break
+            if er or ep:
+                if er and ep:
+                    stats["both_raise"] += 1
+                else:
+                    fails.append((where, "ref %r / prod %r" % (out[0] if er else "ok", out[1] if ep else "ok")))
+                break
+            stats["ops"] += 1
+            if args[0] in ("Reshape", "View", "Contiguous"):
+                r, p = out
+            if args[0] == "CombineBonds" and args[2].get("permute_back") and \
+                    fused_pos(r, args, prev_labels) != 0:
+                # the reference's permute_back never permutes the storage back (`a.Stoarge = ...`, UniTensor.py:4121):
+                # its tensor is inconsistent from here on; compare the metadata only and stop
+                stats["ref_stoarge"] = stats.get("ref_stoarge", 0) + 1
+                if list(r.labels) != list(p.labels) or int(r.rowrank) != int(p.rowrank) or [int(b.dim) for b in r.bonds] != [int(b.dim) for b in p.bonds]:
+                    fails.append((where, "permute_back metadata"))
+                break
+            if not same(r, p, where):
+                break
+    print("seed", seed, stats, "fails", len(fails), "time %.1fs" % (time.time() - t0))
+    seen = set()
+    for f in fails:
+        key = f[1][:40]
+        if key in seen: continue
+        seen.add(key)
+        print("  FAIL", f[0][-420:], "\n       ", f[1][:300])
+        if len(seen) > 10: break
+    return len(fails)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sym"
-    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net}[mode](sys.argv[2:]) else 0)
+    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops}[mode](sys.argv[2:]) else 0)

@@ -585,3 +585,35 @@ def test_permute_without_common_sector_keeps_an_empty_table(T):
     assert np.asarray(q).shape == (0, 1) and np.asarray(t._block_qnums).dtype == np.int64
     with pytest.raises(TypeError):
         t.Contiguous()
+
+
+def test_dense_reshape_view_combine_follow_the_reference(T):
+    """Glue either side of the path, pinned to the reference's behaviour (found by tests/fuzz_vs_reference.py ops):
+    View refuses a non-contiguous tensor and returns a COPY (UniTensor.py:2583-2594); Reshape behaves like
+    torch.reshape on the strided storage (:2404-2406); dense CombineBonds without permute_back leaves the fused
+    bond alone in its space: rowrank 1 when it goes first, rank-1 when it goes last (:4126-4139)."""
+    dev = torch.device(DEV)
+    x = T.UniTensor(bonds=[T.Bond(3), T.Bond(2), T.Bond(4)], rowrank=1, labels=[5, 6, 7], device=dev)
+    x.Storage = torch.arange(24, dtype=torch.float64).reshape(3, 2, 4).to(dev)
+    v = x.View([6, 4], 1)
+    v.Storage[0, 0] = -1.0
+    assert float(x.Storage[0, 0, 0]) == 0.0                      # not an alias
+    x.Permute([1, 0, 2])
+    assert not x.is_contiguous()
+    with pytest.raises(Exception):
+        x.View([6, 4], 1)
+    same_shape = x.Reshape([2, 3, 4], 1)                          # viewable: strides carry over
+    assert not same_shape.is_contiguous()
+    flat = x.Reshape([6, 4], 1)                                   # needs a copy
+    assert flat.is_contiguous()
+    want = torch.arange(24, dtype=torch.float64).reshape(3, 2, 4).permute(1, 0, 2).reshape(6, 4)
+    assert torch.equal(flat.Storage.cpu(), want)
+    y = T.UniTensor(bonds=[T.Bond(2), T.Bond(3), T.Bond(4), T.Bond(5)], rowrank=3, labels=[1, 2, 3, 4], device=dev)
+    y.Storage = torch.arange(120, dtype=torch.float64).reshape(2, 3, 4, 5).to(dev)
+    a = copy.deepcopy(y)
+    a.CombineBonds([3, 1])                                        # first constituent in row space -> fused bond first
+    assert a.labels.tolist() == [3, 2, 4] and a.rowrank == 1 and list(a.shape) == [8, 3, 5]
+    assert torch.equal(a.Storage.cpu(), torch.arange(120, dtype=torch.float64).reshape(2, 3, 4, 5).permute(2, 0, 1, 3).reshape(8, 3, 5))
+    b = copy.deepcopy(y)
+    b.CombineBonds([4, 2])                                        # first constituent in column space -> fused bond last
+    assert b.labels.tolist() == [1, 3, 4] and b.rowrank == 2 and list(b.shape) == [2, 4, 15]

@@ -802,10 +802,20 @@ class UniTensor:
         if not isinstance(dimer, list):
             raise TypeError("UniTensor.%s" % what, "[ERROR] mapper should be an python list.")
 
+    def _reshaped(self, dimer, copy_):
+        """torch.reshape semantics as the reference gets them (UniTensor.py:2404-2406, :2495): when the strided
+        storage can be viewed in the new shape no data moves and the strides (hence `is_contiguous()`) carry over;
+        otherwise the data is laid out afresh -- by the dense permute kernel."""
+        x = self._dense
+        try:
+            v = x.view(dimer)
+        except RuntimeError:
+            return self._contiguous_dense(x).reshape(dimer)
+        return v.clone() if copy_ else v
+
     def Reshape(self, dimer, rowrank, new_labels=None):
         self._reshape_checks(dimer, "Reshape")
-        x = self._contiguous_dense(self._dense)
-        new_Storage = (x.clone() if x is self._dense else x).reshape(dimer)
+        new_Storage = self._reshaped(dimer, True)
         if new_labels is None:
             new_labels = np.arange(len(dimer))
         tmp = UniTensor(bonds=np.array([Bond(dimer[i]) for i in range(len(dimer))]), labels=new_labels,
@@ -815,7 +825,7 @@ class UniTensor:
 
     def Reshape_(self, dimer, rowrank, new_labels=None):
         self._reshape_checks(dimer, "Reshape")
-        self._dense = self._contiguous_dense(self._dense).reshape(dimer)
+        self._dense = self._reshaped(dimer, False)
         if new_labels is None:
             new_labels = np.arange(len(dimer))
         self.labels = np.array(new_labels, dtype=np.int64)
@@ -825,7 +835,10 @@ class UniTensor:
 
     def View(self, dimer, rowrank, new_labels=None):
         self._reshape_checks(dimer, "View")
-        new_Storage = self._dense.view(dimer)
+        if not self.is_contiguous():                                    # UniTensor.py:2583-2585
+            raise Exception("UniTensor.View",
+                            "[ERROR] UniTensor is not contiguous. Call Contiguous_() or Contiguous() before .View()")
+        new_Storage = self._dense.clone().view(dimer)                   # the reference's View copies (:2593-2594)
         if new_labels is None:
             new_labels = np.arange(len(dimer))
         tmp = UniTensor(bonds=np.array([Bond(dimer[i]) for i in range(len(dimer))]), labels=new_labels,
@@ -835,6 +848,9 @@ class UniTensor:
 
     def View_(self, dimer, rowrank, new_labels=None):
         self._reshape_checks(dimer, "View")
+        if not self.is_contiguous():
+            raise Exception("UniTensor.View",
+                            "[ERROR] UniTensor is not contiguous. Call Contiguous_() or Contiguous() before .View()")
         self._dense = self._dense.view(dimer)
         if new_labels is None:
             new_labels = np.arange(len(dimer))
@@ -1310,7 +1326,6 @@ def _CombineBonds(a, idxs, new_label, permute_back):
     else:
         # combined bond goes first if idxs[0] is in row space, else last (UniTensor.py:4126-4180)
         to_front = idxs[0] < a.rowrank
-        n_row = int(np.sum(idx_no_combine < a.rowrank))
         if to_front:
             order = list(idxs) + list(idx_no_combine)
             shp = [combined_dim] + list(old_shape[idx_no_combine])
@@ -1318,7 +1333,7 @@ def _CombineBonds(a, idxs, new_label, permute_back):
             a.bonds = np.array([new_bond] + list(a.bonds[idx_no_combine]), dtype=object)
             if a.braket is not None:
                 a.braket = np.concatenate([a.braket[idxs[:1]], a.braket[idx_no_combine]])
-            a.rowrank = n_row + 1
+            a.rowrank = 1                                   # UniTensor.py:4139, :4180: the fused bond alone in row space
         else:
             order = list(idx_no_combine) + list(idxs)
             shp = list(old_shape[idx_no_combine]) + [combined_dim]
@@ -1326,7 +1341,7 @@ def _CombineBonds(a, idxs, new_label, permute_back):
             a.bonds = np.array(list(a.bonds[idx_no_combine]) + [new_bond], dtype=object)
             if a.braket is not None:
                 a.braket = np.concatenate([a.braket[idx_no_combine], a.braket[idxs[:1]]])
-            a.rowrank = n_row
+            a.rowrank = len(a.labels) - 1                   # :4132, :4172: the fused bond alone in column space
         x = UniTensor._contiguous_dense(a._dense.permute(*[int(i) for i in order]))
         a._dense = x.reshape([int(s) for s in shp])
     a._check_braket()
