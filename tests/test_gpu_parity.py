@@ -617,3 +617,37 @@ def test_dense_reshape_view_combine_follow_the_reference(T):
     b = copy.deepcopy(y)
     b.CombineBonds([4, 2])                                        # first constituent in column space -> fused bond last
     assert b.labels.tolist() == [1, 3, 4] and b.rowrank == 2 and list(b.shape) == [2, 4, 15]
+
+
+def test_whole_transpose_follows_the_reference(T):
+    """UniTensor.py:1386-1423 (found by tests/fuzz_vs_reference.py symops): a transposed COPY -- row and column spaces
+    swapped, bra/ket tags exchanged on tagged tensors, `self` untouched; on a symmetric tensor the relaid-out result
+    holds the transposed blocks under the same sector table."""
+    dev = torch.device(DEV)
+    x = T.UniTensor(bonds=[T.Bond(2), T.Bond(3), T.Bond(4)], rowrank=1, labels=[5, 6, 7], device=dev)
+    x.Storage = torch.arange(24, dtype=torch.float64).reshape(2, 3, 4).to(dev)
+    y = x.Whole_transpose()
+    assert x.labels.tolist() == [5, 6, 7] and x.rowrank == 1
+    assert y.labels.tolist() == [6, 7, 5] and y.rowrank == 2 and list(y.shape) == [3, 4, 2]
+    assert torch.equal(y.Storage.contiguous().cpu(), torch.arange(24, dtype=torch.float64).reshape(2, 3, 4).permute(1, 2, 0))
+    t = T.UniTensor(bonds=[T.Bond(2, T.BD_KET), T.Bond(3, T.BD_BRA)], rowrank=1, labels=[1, 2], device=dev)
+    u = t.Whole_transpose()
+    assert [b.bondType for b in t.bonds] == [T.BD_KET, T.BD_BRA]
+    assert u.labels.tolist() == [2, 1] and [b.bondType for b in u.bonds] == [T.BD_KET, T.BD_BRA] and u.braket.tolist() == [-1, 1]
+    u1 = [T.Symmetry.U1()]
+    s = T.UniTensor(bonds=[T.Bond(3, T.BD_KET, qnums=[[1], [0], [-1]], sym_types=u1),
+                           T.Bond(2, T.BD_KET, qnums=[[1], [0]], sym_types=u1),
+                           T.Bond(4, T.BD_BRA, qnums=[[2], [1], [0], [-1]], sym_types=u1)],
+                    rowrank=2, labels=[1, 2, 3], device=dev)
+    for i in range(len(s.Storage)):
+        s.Storage[i] = (torch.arange(s.Storage[i].numel(), dtype=torch.float64).reshape(s.Storage[i].shape) + 10 * i).to(dev)
+    before = [b.clone() for b in s.Storage]
+    tr = s.Whole_transpose()
+    assert not tr.is_contiguous()
+    w = tr.Contiguous()
+    assert w.labels.tolist() == [3, 1, 2] and w.rowrank == 1 and w.braket.tolist() == [-1, 1, 1]
+    assert np.array_equal(w._block_qnums, s._block_qnums)
+    for a, b in zip(before, w.Storage):
+        assert torch.equal(a.t().contiguous(), b)
+    for a, b in zip(before, s.Storage):
+        assert torch.equal(a, b)

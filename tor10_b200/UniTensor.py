@@ -197,7 +197,8 @@ class UniTensor:
     def _layout_current(self):
         """True when the arena is laid out for the CURRENT bond order and row/col split.  The reference only
         tracks the bond order (`_contiguous`, quirk Q1); here a changed rowrank also counts as "needs relayout"."""
-        return self._contiguous and self.rowrank == self._layout.rowrank
+        return (self._contiguous and self.rowrank == self._layout.rowrank
+                and np.array_equal(self._layout.braket, self.braket))     # tags exchanged (Whole_transpose): relayout
 
     def _logical_layout(self):
         return _plan.get_layout(list(self.bonds), self.braket, self.rowrank, self._arena.device)
@@ -657,10 +658,16 @@ class UniTensor:
         return self._inplace(other, torch.mul, "*")
 
     def Whole_transpose(self):
-        """Swap row and column spaces (UniTensor.py:1386-1425)."""
-        n = len(self.bonds)
-        self.Permute(list(range(self.rowrank, n)) + list(range(self.rowrank)), rowrank=n - self.rowrank)
-        return self
+        """A transposed COPY (UniTensor.py:1386-1423): row and column spaces swapped; on a tagged tensor (symmetric
+        or not) every bond's bra/ket tag is exchanged as well.  `self` is left as it is."""
+        out = copy.deepcopy(self)
+        if out.braket is not None:
+            for b in out.bonds:
+                b.change(BD_BRA if b.bondType == BD_KET else BD_KET)
+            out.braket = out.braket * -1
+        n = len(out.bonds)
+        out.Permute(list(range(out.rowrank, n)) + list(range(out.rowrank)), rowrank=n - out.rowrank)
+        return out
 
     # ------------------------------------------------------------------ linalg wrappers
     def Svd(self):
