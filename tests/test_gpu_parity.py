@@ -651,3 +651,42 @@ def test_whole_transpose_follows_the_reference(T):
         assert torch.equal(a.t().contiguous(), b)
     for a, b in zip(before, s.Storage):
         assert torch.equal(a, b)
+
+
+def test_contract_of_transposed_operands(T):
+    """(A.B)^T = B^T.A^T through Whole_transpose: the operands carry exchanged bra/ket tags, so their stored sector
+    tables no longer describe them even where the bond order is back to the stored one -- Contract must relayout
+    instead of reading them in place (the reference keeps stale blocks in that state)."""
+    A, B = _c3_spec(48, -3, 3, 1.5)
+    a, b = psym(T, A, seed=61, device=DEV), psym(T, B, seed=62, device=DEV)
+    c = T.Contract(a, b)
+    ct = T.Contract(b.Whole_transpose(), a.Whole_transpose())
+    want = c.Whole_transpose()
+    want.Permute([int(x) for x in ct.labels], rowrank=int(ct.rowrank), by_label=True)
+    want = want.Contiguous()
+    got = ct if ct.is_contiguous() else ct.Contiguous()
+    assert np.array_equal(got._block_qnums, want._block_qnums) and len(got.Storage) > 3
+    for x, y in zip(got.Storage, want.Storage):
+        assert x.shape == y.shape and float((x - y).abs().max()) <= 1e-13 * float(y.abs().max())
+    # the case the in-place test of ContractPlan must not fall for: A stored as [(k) ; (i)], so that A^T as second
+    # operand needs exactly the stored bond order and row/column split -- but under exchanged tags
+    u1 = [["U1", 0]]
+    A2 = {"bonds": [{"dim": 3, "btype": 1, "qnums": [[1], [-1], [-2]], "syms": u1},
+                    {"dim": 3, "btype": -1, "qnums": [[2], [1], [-2]], "syms": u1}], "labels": [20, 0], "rowrank": 1}
+    B2 = {"bonds": [{"dim": 3, "btype": -1, "qnums": [[1], [-1], [-2]], "syms": u1},
+                    {"dim": 2, "btype": 1, "qnums": [[1], [1]], "syms": u1}], "labels": [20, 40], "rowrank": 1}
+    a2, b2 = psym(T, A2, seed=2, device=DEV), psym(T, B2, seed=501, device=DEV)
+    c2 = T.Contract(a2, b2).Whole_transpose()
+    ct2 = T.Contract(b2.Whole_transpose(), a2.Whole_transpose())
+    c2.Permute([int(x) for x in ct2.labels], rowrank=int(ct2.rowrank), by_label=True)
+    c2 = c2.Contiguous()
+    ct2 = ct2 if ct2.is_contiguous() else ct2.Contiguous()
+    assert np.array_equal(c2._block_qnums, ct2._block_qnums)
+    for x, y in zip(ct2.Storage, c2.Storage):
+        assert x.shape == y.shape and float((x - y).abs().max()) <= 1e-13 * max(1.0, float(y.abs().max()))
+    # a transposed-back tensor equals the original bit for bit
+    back = a.Whole_transpose().Whole_transpose()
+    back.Permute([int(x) for x in a.labels], rowrank=int(a.rowrank), by_label=True)
+    back = back.Contiguous()
+    for x, y in zip(back.Storage, a.Storage):
+        assert torch.equal(x, y)

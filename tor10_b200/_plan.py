@@ -679,8 +679,9 @@ class ContractPlan:
         self.La, self.Lb, self.Lo = La, Lb, Lo
         # the reference tests only `_mapper == identity` (quirk Q1); a changed rowrank with identity
         # mapper leaves its Storage stale.  Here the relayout runs whenever the memory layout differs.
-        ident_a = (map_a == np.arange(len(map_a))).all() and rr_a == Ma.rowrank
-        ident_b = (map_b == np.arange(len(map_b))).all() and rr_b == Mb.rowrank
+        # (exchanged bra/ket tags -- Whole_transpose -- also change the sector table: compare them too)
+        ident_a = (map_a == np.arange(len(map_a))).all() and rr_a == Ma.rowrank and np.array_equal(Ma.braket, bk_a)
+        ident_b = (map_b == np.arange(len(map_b))).all() and rr_b == Mb.rowrank and np.array_equal(Mb.braket, bk_b)
         # sector matching (UniTensor.py:3727-3738)
         matched = []
         for ob in range(Lo.nsec):
