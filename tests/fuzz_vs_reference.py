@@ -22,6 +22,9 @@ as shipped (compatibility shim of tests/golden/make_golden.py).  Random inputs, 
     python tests/fuzz_vs_reference.py symops <seed> <cases>      random sequences on SYMMETRIC tensors: Permute (index /
                                                                  label), Contiguous, scalar and tensor arithmetic,
                                                                  Whole_transpose, GetTotalQnums, GetValidQnums, SetLabels
+    python tests/fuzz_vs_reference.py ctor   <seed> <cases>      Bond and UniTensor constructors with valid AND invalid
+                                                                 arguments (same exception class, same object), Bond
+                                                                 combine / == / change, GetUniqueQnums, GetDegeneracy
     python tests/fuzz_vs_reference.py linalg <seed> <cases>      + - * / between dense / diagonal tensors and scalars,
                                                                  Svd_truncate, Qr, Inverse, Det, Norm, ExpH, Abs, Mean,
                                                                  Otimes, Todense, Whole_transpose (metadata; values,
@@ -42,6 +45,8 @@ symops, seeds 1..4 x 2000 (12 374 operations): found and fixed -- Whole_transpos
 bra/ket tags exchanged (it used to permute in place), and a tensor whose tags changed counts as "needs relayout".
 Reference states that are stale by construction are skipped: identity mapper with another rowrank (quirk Q1, 10
 sequences) or with exchanged tags (73), inputs that lose elements (quirk Q3, 493).
+ctor, seeds 2..4 x 10 000 (+ 2 x 5 000 with the Bond API): 40 000 Bond and 40 000 UniTensor constructions, 60 % of
+them invalid on purpose, 10 000 Bond API calls -- same exception class or same object every time.
 linalg, seeds 1..3 x 1000: 17 functions x 3 000 calls, no discrepancy (Otimes with a diagonal operand raises inside
 torch in the reference and works here).
 """
@@ -844,6 +849,158 @@ def fuzz_symops(argv):
     return len(fails)
 
 
+def fuzz_ctor(argv):
+    seed, ncase = int(argv[0]) if len(argv) > 0 else 1, int(argv[1]) if len(argv) > 1 else 300
+    rng = np.random.default_rng(seed)
+    fails, stats = [], {"ctor_ok": 0, "ctor_raise_both": 0, "bond_ok": 0, "bond_raise_both": 0, "ref_bug": 0}
+    t0 = time.time()
+
+    def mk_bond(lib, spec):
+        BT = {1: lib.BD_BRA, -1: lib.BD_KET, 0: lib.BD_REG}
+        kw = {}
+        if spec.get("qnums") is not None:
+            kw["qnums"] = spec["qnums"]
+            if spec.get("syms") is not None:
+                kw["sym_types"] = [lib.Symmetry.U1() if s[0] == "U1" else lib.Symmetry.Zn(s[1]) for s in spec["syms"]]
+        return lib.Bond(spec["dim"], BT[spec["btype"]], **kw)
+
+    def cls(e):
+        return type(e).__name__ if isinstance(e, Exception) else "ok"
+
+    for it in range(ncase):
+        # ---- Bond constructor / API
+        nsym = int(rng.integers(1, 3))
+        syms = [["U1", 0] if rng.random() < 0.5 else ["Zn", int(rng.integers(2, 5))] for _ in range(nsym)]
+        dim = int(rng.integers(-1, 6))
+        bt = int(rng.choice([-1, 0, 1]))
+        has_q = rng.random() < 0.7
+        q = None
+        if has_q:
+            rows = dim if rng.random() < 0.85 else max(0, dim + int(rng.choice([-1, 1])))
+            cols = nsym if rng.random() < 0.9 else nsym + 1
+            q = [[int(rng.integers(-3, 5)) for _ in range(cols)] for _ in range(max(rows, 0))]
+        spec = {"dim": dim, "btype": bt, "qnums": q, "syms": syms if (has_q and rng.random() < 0.8) else None}
+        out = []
+        for lib in (ref, T):
+            try:
+                out.append(mk_bond(lib, spec))
+            except Exception as e:
+                out.append(e)
+        r, p = out
+        if isinstance(r, (NameError, AttributeError, UnboundLocalError)):
+            stats["ref_bug"] += 1
+        elif isinstance(r, Exception) != isinstance(p, Exception):
+            fails.append(("bond %s" % spec, "ref %s / prod %s (%r | %r)" % (cls(r), cls(p), r if isinstance(r, Exception) else "", p if isinstance(p, Exception) else "")))
+        elif isinstance(r, Exception):
+            stats["bond_raise_both"] += 1
+            if type(r).__name__ != type(p).__name__ and not isinstance(p, type(r)):
+                fails.append(("bond %s" % spec, "exception class ref %s / prod %s" % (cls(r), cls(p))))
+        else:
+            stats["bond_ok"] += 1
+            rq, pq = r.qnums, p.qnums
+            if (rq is None) != (pq is None) or (rq is not None and not np.array_equal(np.asarray(rq), np.asarray(pq))) or int(r.dim) != int(p.dim):
+                fails.append(("bond %s" % spec, "qnums/dim"))
+            elif rq is not None:
+                try:
+                    ru, pu = r.GetUniqueQnums(), p.GetUniqueQnums()
+                    if not np.array_equal(np.asarray(ru), np.asarray(pu)):
+                        fails.append(("bond %s" % spec, "unique qnums"))
+                    qq = np.asarray(rq)[int(rng.integers(0, len(rq)))].tolist() if len(rq) else None
+                    if qq is not None:
+                        rd, pd = r.GetDegeneracy(*qq), p.GetDegeneracy(*qq)
+                        if int(rd) != int(pd):
+                            fails.append(("bond %s" % spec, "degeneracy %s: %s vs %s" % (qq, rd, pd)))
+                except Exception as e:
+                    fails.append(("bond %s" % spec, "api raised %r" % (e,)))
+        # ---- Bond.combine / == / change on valid bonds
+        nb = int(rng.integers(2, 4))
+        symsv = [["U1", 0] if rng.random() < 0.5 else ["Zn", int(rng.integers(2, 5))] for _ in range(int(rng.integers(1, 3)))]
+        specs = []
+        for _ in range(nb):
+            d = int(rng.integers(1, 4))
+            symq = rng.random() < 0.8
+            specs.append({"dim": d, "btype": int(rng.choice([-1, 1])) if symq else int(rng.choice([-1, 0, 1])),
+                          "qnums": [[int(rng.integers(0, 2)) if sy[0] == "Zn" else int(rng.integers(-2, 3)) for sy in symsv] for _ in range(d)] if symq else None,
+                          "syms": symsv if symq else None})
+        how = str(rng.choice(["single", "list", "eq", "change"]))
+        out = []
+        for lib in (ref, T):
+            try:
+                bs = [mk_bond(lib, sp) for sp in specs]
+                if how == "single":
+                    bs[0].combine(bs[1]); out.append(bs[0])
+                elif how == "list":
+                    bs[0].combine(bs[1:]); out.append(bs[0])
+                elif how == "eq":
+                    out.append((bs[0] == bs[1], bs[0] == mk_bond(lib, specs[0])))
+                else:
+                    bs[0].change({1: lib.BD_BRA, -1: lib.BD_KET, 0: lib.BD_REG}[int(specs[1]["btype"])]); out.append(bs[0])
+            except Exception as e:
+                out.append(e)
+        r, p = out
+        stats["bond_api"] = stats.get("bond_api", 0) + 1
+        if isinstance(r, (NameError, AttributeError, UnboundLocalError)):
+            stats["ref_bug"] += 1
+        elif isinstance(r, Exception) != isinstance(p, Exception):
+            fails.append(("bondapi %s %s" % (how, specs), "ref %s / prod %s (%r | %r)" % (cls(r), cls(p), r if isinstance(r, Exception) else "", p if isinstance(p, Exception) else "")))
+        elif isinstance(r, Exception):
+            pass
+        elif how == "eq":
+            if tuple(bool(x) for x in r) != tuple(bool(x) for x in p):
+                fails.append(("bondapi eq %s" % specs, "%s vs %s" % (r, p)))
+        else:
+            same_q = (r.qnums is None) == (p.qnums is None) and (r.qnums is None or np.array_equal(np.asarray(r.qnums), np.asarray(p.qnums)))
+            tmap = {ref.BD_BRA: T.BD_BRA, ref.BD_KET: T.BD_KET, ref.BD_REG: T.BD_REG}
+            if not same_q or int(r.dim) != int(p.dim) or tmap[r.bondType] != p.bondType:
+                fails.append(("bondapi %s %s" % (how, specs), "result differs"))
+        # ---- UniTensor constructor (dense / tagged), valid and invalid argument combinations
+        rank = int(rng.integers(0, 5))
+        dims = [int(rng.integers(1, 4)) for _ in range(rank)]
+        mode = str(rng.choice(["untagged", "tagged", "mixed"]))
+        if mode == "untagged": bts = [0] * rank
+        elif mode == "tagged": bts = [int(x) for x in rng.choice([-1, 1], size=rank)]
+        else: bts = [int(x) for x in rng.choice([-1, 0, 1], size=rank)]
+        rr = None if rng.random() < 0.3 else int(rng.integers(-1, rank + 2))
+        labels = None if rng.random() < 0.4 else [int(x) for x in rng.integers(-2, 6, size=rank if rng.random() < 0.9 else rank + 1)]
+        diag = rng.random() < 0.2
+        args = dict(rowrank=rr, labels=labels, is_diag=diag)
+        if rng.random() < 0.1: args.pop("rowrank")
+        out = []
+        for lib in (ref, T):
+            BT = {1: lib.BD_BRA, -1: lib.BD_KET, 0: lib.BD_REG}
+            kw = dict(args)
+            if lib is T: kw["device"] = torch.device("cpu")
+            try:
+                out.append(lib.UniTensor(bonds=[lib.Bond(d, BT[b]) for d, b in zip(dims, bts)], **kw))
+            except Exception as e:
+                out.append(e)
+        r, p = out
+        where = "ctor dims%s bts%s %s" % (dims, bts, args)
+        if isinstance(r, (NameError, AttributeError, UnboundLocalError)):
+            stats["ref_bug"] += 1
+        elif isinstance(r, Exception) != isinstance(p, Exception):
+            fails.append((where, "ref %s / prod %s (%r | %r)" % (cls(r), cls(p), r if isinstance(r, Exception) else "", p if isinstance(p, Exception) else "")))
+        elif isinstance(r, Exception):
+            stats["ctor_raise_both"] += 1
+            if type(r).__name__ != type(p).__name__ and not isinstance(p, type(r)):
+                fails.append((where, "exception class ref %s / prod %s" % (cls(r), cls(p))))
+        else:
+            stats["ctor_ok"] += 1
+            ok = (list(r.labels) == list(p.labels) and int(r.rowrank) == int(p.rowrank) and bool(r.is_diag) == bool(p.is_diag)
+                  and (r.braket is None) == (p.braket is None) and (r.braket is None or list(r.braket) == list(p.braket))
+                  and tuple(r.Storage.shape) == tuple(p.Storage.shape) and bool(r.is_braket) == bool(p.is_braket))
+            if not ok:
+                fails.append((where, "meta ref labels %s rr %s braket %s shape %s is_braket %s / prod %s %s %s %s %s" % (list(r.labels), r.rowrank, r.braket, tuple(r.Storage.shape), r.is_braket, list(p.labels), p.rowrank, p.braket, tuple(p.Storage.shape), p.is_braket)))
+    print("seed", seed, stats, "fails", len(fails), "time %.1fs" % (time.time() - t0))
+    seen = set()
+    for f in fails:
+        key = f[1][:60]
+        if key in seen: continue
+        seen.add(key); print("  FAIL", f[0][:230], "\n      ", f[1][:330])
+        if len(seen) > 12: break
+    return len(fails)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sym"
-    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops}[mode](sys.argv[2:]) else 0)
+    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops, "ctor": fuzz_ctor}[mode](sys.argv[2:]) else 0)
