@@ -938,6 +938,8 @@ class UniTensor:
         these charges is overwritten (non-contiguous tensors scatter through the relayout kernel)."""
         if not isinstance(block, self.__class__):
             raise TypeError("UniTensor.PutBlock", "[ERROR] the block can only be an UniTensor")
+        if block.braket is not None:                                       # UniTensor.py:2939-2940
+            raise Exception("[ERROR] PutBlock can only accept a untagged UniTensor ")
         if not self.is_symm:
             if len(qnum):
                 raise TypeError("UniTensor.PutBlock", "[ERROR] Cannot put block with qnums on a non-symmetry tensor")
