@@ -29,6 +29,9 @@ as shipped (compatibility shim of tests/golden/make_golden.py).  Random inputs, 
                                                                  wrong block shape, tagged block, SetRowRank out of
                                                                  range, Todense, Reshape, duplicate labels, Contract with
                                                                  a dense tensor, ...): same exception class
+    python tests/fuzz_vs_reference.py denseapi <seed> <cases>    small API of dense tensors, right and wrong usage:
+                                                                 GetBlock / PutBlock, SetElem, Todense, SetLabel,
+                                                                 From_torch, Matmul with mismatching shapes, ...
     python tests/fuzz_vs_reference.py linalg <seed> <cases>      + - * / between dense / diagonal tensors and scalars,
                                                                  Svd_truncate, Qr, Inverse, Det, Norm, ExpH, Abs, Mean,
                                                                  Otimes, Todense, Whole_transpose (metadata; values,
@@ -52,6 +55,11 @@ sequences) or with exchanged tags (73), inputs that lose elements (quirk Q3, 493
 ctor, seeds 2..4 x 10 000 (+ 2 x 5 000 with the Bond API): 40 000 Bond and 40 000 UniTensor constructions, 60 % of
 them invalid on purpose, 10 000 Bond API calls -- same exception class or same object every time.
 symerr, seeds 1..3 x 2500 (14 898 calls, 97 % of them must raise): found and fixed -- PutBlock refuses a tagged block.
+denseapi, seeds 1..3 x 8000: found and fixed -- dense GetBlock / PutBlock shapes (rank-1 block when a space is
+empty, charges ignored), Matmul / the dense GEMM raise RuntimeError on mismatching inner dimensions (they computed
+with the wrong K), Svd / Qr / Qdr label their new bonds by the reference's position rule.  Not compared: rank-2
+functions called with other ranks (the reference does not validate, torch decides), From_torch(is_tag=True) (tagged
+bonds but `braket` None in the reference).
 linalg, seeds 1..3 x 1000: 17 functions x 3 000 calls, no discrepancy (Otimes with a diagonal operand raises inside
 torch in the reference and works here).
 """
@@ -1096,6 +1104,112 @@ def fuzz_symerr(argv):
     return len(fails)
 
 
+def fuzz_denseapi(argv):
+    seed, ncase = int(argv[0]) if len(argv) > 0 else 1, int(argv[1]) if len(argv) > 1 else 300
+    rng = np.random.default_rng(seed)
+    fails, stats = [], {"calls": 0, "both_raise": 0, "ok": 0, "ref_bug": 0}
+    t0 = time.time()
+    def cls(e): return type(e).__name__ if isinstance(e, Exception) else "ok"
+    KINDS = ["getblock", "getblock_q", "putblock", "putblock_shape", "setelem", "setelem_len", "todense", "todense_", "setlabel", "setlabel_dup",
+             "setname", "matmul_rank", "matmul_shape", "contract_nonut", "svd_rank3", "inverse_nonsq", "det_rank3", "from_torch", "from_torch_bad",
+             "permute_label_bad", "permute_len", "combine_one", "combine_missing", "pow", "neg_index_getblock", "chain_matmul_bad", "exph_nonsq", "shape", "dtype_dev"]
+    for it in range(ncase):
+        rank = int(rng.integers(0, 4))
+        dims = [int(rng.integers(1, 4)) for _ in range(rank)]
+        diag = rank == 2 and dims[0] == dims[1] and rng.random() < 0.3
+        rr = 1 if diag else int(rng.integers(0, rank + 1))
+        tagged = (not diag) and rank > 0 and rng.random() < 0.3
+        bts = ([-1] * rr + [1] * (rank - rr)) if tagged else [0] * rank
+        labels = [int(x) for x in rng.permutation(np.arange(-3, 9))[:rank]]
+        vals = rng.random(dims[0] if diag else tuple(dims))
+        def mk(lib):
+            BT = {1: lib.BD_BRA, -1: lib.BD_KET, 0: lib.BD_REG}
+            kw = {} if lib is ref else {"device": torch.device("cpu")}
+            t = lib.UniTensor(bonds=[lib.Bond(d, BT[b]) for d, b in zip(dims, bts)], rowrank=rr, labels=labels, is_diag=diag, **kw)
+            t.Storage = torch.from_numpy(np.array(vals).copy())
+            return t
+        kind = str(rng.choice(KINDS))
+        aux = rng.random((3, 3)); k1 = int(rng.integers(0, 5)); k2 = int(rng.integers(-2, 9))
+        def call(lib):
+            kw = {} if lib is ref else {"device": torch.device("cpu")}
+            t = mk(lib)
+            if kind == "getblock": return t.GetBlock()
+            if kind == "getblock_q": return t.GetBlock(0)
+            if kind == "putblock": b = mk(lib); return t.PutBlock(b) or t
+            if kind == "putblock_shape":
+                b = lib.UniTensor(bonds=[lib.Bond(5), lib.Bond(2)], rowrank=1, **kw); return t.PutBlock(b) or t
+            if kind == "setelem": t.SetElem(list(np.arange(int(np.prod(t.Storage.shape)), dtype=float))); return t
+            if kind == "setelem_len": t.SetElem([1.0] * (int(np.prod(t.Storage.shape)) + 1)); return t
+            if kind == "todense": return t.Todense()
+            if kind == "todense_": t.Todense_(); return t
+            if kind == "setlabel": t.SetLabel(k2, k1); return t
+            if kind == "setlabel_dup": t.SetLabel(labels[0] if labels else 0, 1); return t
+            if kind == "setname": t.SetName("x" if k1 else 3); return t
+            if kind == "matmul_rank": return lib.Matmul(t, t)
+            if kind == "matmul_shape":
+                b = lib.UniTensor(bonds=[lib.Bond(4), lib.Bond(2)], rowrank=1, **kw); return lib.Matmul(t, b)
+            if kind == "contract_nonut": return lib.Contract(t, 3)
+            if kind == "svd_rank3": return lib.Svd(t)[1]
+            if kind == "inverse_nonsq": return lib.Inverse(t)
+            if kind == "det_rank3": return lib.Det(t)
+            if kind == "from_torch": return lib.From_torch(torch.from_numpy(aux.copy()), rowrank=min(k1, 2), labels=[4, 5] if k1 % 2 else None, is_tag=bool(k1 % 3 == 0))
+            if kind == "from_torch_bad": return lib.From_torch(torch.from_numpy(aux.copy()), rowrank=k1 + 1, labels=[1, 2, 3][:k1 % 4])
+            if kind == "permute_label_bad": return t.Permute([77] * rank, by_label=True)
+            if kind == "permute_len": return t.Permute(list(range(rank + 1)))
+            if kind == "combine_one": t.CombineBonds(labels[:1]); return t
+            if kind == "combine_missing": t.CombineBonds([labels[0] if labels else 0, 99]); return t
+            if kind == "pow": return t ** 2
+            if kind == "neg_index_getblock": return t.GetBlock(-1)
+            if kind == "chain_matmul_bad": return lib.Chain_matmul(t, t, 3)
+            if kind == "exph_nonsq": return lib.ExpH(t)
+            if kind == "shape": return list(t.shape)
+            if kind == "dtype_dev": return (str(t.dtype), str(t.device), bool(t.is_contiguous()), bool(t.is_braket) if t.is_braket is not None else None)
+        out = []
+        for lib in (ref, T):
+            try:
+                out.append(call(lib))
+            except Exception as e:
+                out.append(e)
+        stats["calls"] += 1
+        er, ep = isinstance(out[0], Exception), isinstance(out[1], Exception)
+        where = "%s rank%d dims%s rr%d diag%d tagged%d" % (kind, rank, dims, rr, diag, tagged)
+        if isinstance(out[0], (NameError, AttributeError, UnboundLocalError)):
+            stats["ref_bug"] += 1; continue
+        misuse_rank = kind in ("matmul_rank", "matmul_shape", "svd_rank3", "inverse_nonsq", "det_rank3", "exph_nonsq", "chain_matmul_bad") and (rank != 2 or rr != 1 or diag or tagged)
+        if misuse_rank or (kind == "permute_label_bad" and rank == 0):
+            stats["misuse_skipped"] = stats.get("misuse_skipped", 0) + 1      # the reference does not validate; torch decides
+            continue
+        if kind == "from_torch" and k1 % 3 == 0:
+            stats["from_torch_tag"] = stats.get("from_torch_tag", 0) + 1      # reference: tagged bonds but braket None
+            continue
+        if er != ep:
+            fails.append((where, "ref %s / prod %s (%r | %r)" % (cls(out[0]), cls(out[1]), out[0] if er else "", out[1] if ep else ""))); continue
+        if er:
+            stats["both_raise"] += 1
+            if type(out[0]).__name__ != type(out[1]).__name__ and not isinstance(out[1], type(out[0])):
+                fails.append((where, "exception class ref %s / prod %s (%r | %r)" % (cls(out[0]), cls(out[1]), out[0], out[1])))
+            continue
+        stats["ok"] += 1
+        r, p = out
+        if hasattr(r, "Storage"):
+            x, y = r.Storage.contiguous().numpy(), p.Storage.contiguous().cpu().numpy()
+            ok = (list(r.labels) == list(p.labels) and int(r.rowrank) == int(p.rowrank) and bool(r.is_diag) == bool(p.is_diag)
+                  and x.shape == y.shape and (x.size == 0 or np.allclose(x, y, rtol=1e-10, atol=1e-12, equal_nan=True))
+                  and (r.braket is None) == (p.braket is None) and getattr(r, "name", "") == getattr(p, "name", ""))
+            if not ok:
+                fails.append((where, "result: ref %s rr%d diag%d %s / prod %s rr%d diag%d %s" % (list(r.labels), r.rowrank, r.is_diag, x.shape, list(p.labels), p.rowrank, p.is_diag, y.shape)))
+        elif isinstance(r, (list, tuple)):
+            if list(r) != list(p): fails.append((where, "value %s vs %s" % (r, p)))
+    print("seed", seed, stats, "fails", len(fails), "time %.1fs" % (time.time() - t0))
+    seen = set()
+    for f in fails:
+        key = (f[0].split(" ")[0], f[1][:45])
+        if key in seen: continue
+        seen.add(key); print("  FAIL", f[0], "|", f[1][:420])
+        if len(seen) > 16: break
+    return len(fails)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sym"
-    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops, "ctor": fuzz_ctor, "symerr": fuzz_symerr}[mode](sys.argv[2:]) else 0)
+    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops, "ctor": fuzz_ctor, "symerr": fuzz_symerr, "denseapi": fuzz_denseapi}[mode](sys.argv[2:]) else 0)

@@ -690,3 +690,37 @@ def test_contract_of_transposed_operands(T):
     back = back.Contiguous()
     for x, y in zip(back.Storage, a.Storage):
         assert torch.equal(x, y)
+
+
+def test_dense_blocks_and_shape_checks_follow_the_reference(T):
+    """Found by tests/fuzz_vs_reference.py denseapi.  Dense GetBlock / PutBlock (UniTensor.py:3169-3195, :2941-2971):
+    a rank-1 block when the row or the column space is empty, [rows, cols] otherwise, charges ignored.  Matmul with
+    mismatching inner dimensions raises RuntimeError (torch.matmul in the reference) instead of running the GEMM with
+    the wrong K; Svd labels its new bonds by the reference's position rule (linalg.py:535-539)."""
+    dev = torch.device(DEV)
+    x = T.UniTensor(bonds=[T.Bond(2), T.Bond(3), T.Bond(2)], rowrank=2, labels=[0, 1, 2], device=dev)
+    x.Storage = torch.arange(12, dtype=torch.float64).reshape(2, 3, 2).to(dev)
+    b = x.GetBlock()
+    assert list(b.shape) == [6, 2] and b.rowrank == 1 and b.labels.tolist() == [0, 1]
+    assert list(x.GetBlock(7).shape) == [6, 2]                      # charges are ignored on a dense tensor
+    x.SetRowRank(0)
+    b0 = x.GetBlock()
+    assert list(b0.shape) == [12] and b0.rowrank == 0
+    x.SetRowRank(3)
+    b3 = x.GetBlock()
+    assert list(b3.shape) == [12] and b3.rowrank == 1
+    b3.Storage = b3.Storage * 2
+    x.PutBlock(b3)
+    assert torch.equal(x.Storage.cpu(), 2 * torch.arange(12, dtype=torch.float64).reshape(2, 3, 2))
+    with pytest.raises(Exception):
+        x.PutBlock(b)                                               # [6, 2] no longer is the block's shape
+    m1 = T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], rowrank=1, device=dev)
+    m2 = T.UniTensor(bonds=[T.Bond(5), T.Bond(2)], rowrank=1, device=dev)
+    with pytest.raises(RuntimeError):
+        T.Matmul(m1, m2)
+    with pytest.raises(RuntimeError):
+        T.Chain_matmul(m1, m2)
+    y = T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], rowrank=1, labels=[5, -7], device=dev)
+    y.Storage = torch.arange(12, dtype=torch.float64).reshape(3, 4).to(dev)
+    u, s, v = T.Svd(y)
+    assert u.labels.tolist() == [5, 0] and s.labels.tolist() == [0, -1] and v.labels.tolist() == [-1, -7]

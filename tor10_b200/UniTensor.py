@@ -941,11 +941,19 @@ class UniTensor:
         if block.braket is not None:                                       # UniTensor.py:2939-2940
             raise Exception("[ERROR] PutBlock can only accept a untagged UniTensor ")
         if not self.is_symm:
-            if len(qnum):
-                raise TypeError("UniTensor.PutBlock", "[ERROR] Cannot put block with qnums on a non-symmetry tensor")
-            if self.is_diag != block.is_diag or tuple(self.shape) != tuple(block.shape):
-                raise Exception("UniTensor.PutBlock", "[ERROR] block shape / is_diag does not match the tensor")
-            self._dense = block._dense.clone()
+            # UniTensor.py:2941-2971: the block has the shape GetBlock returns; charges, if given, are ignored
+            if self.is_diag and not block.is_diag:
+                raise Exception("[ERROR] PutBlock for a is_diag=True tensor can only accept a block with is_diag=True")
+            n = int(self._dense.numel())
+            if self.rowrank == 0 or len(self.bonds) - self.rowrank == 0:
+                want = (n,)
+            else:
+                r = int(np.prod([b.dim for b in self.bonds[:self.rowrank]], dtype=np.int64))
+                want = (r, int(np.prod([b.dim for b in self.bonds[self.rowrank:]], dtype=np.int64)))
+            if tuple(block.shape) != want:
+                raise Exception("[ERROR] the shape of input Block", block.shape,
+                                "does not match the shape of current block", torch.Size(want))
+            self._dense = block._dense.clone().reshape(self._dense.shape)
             return
         if block.is_symm or block.is_diag or len(block.bonds) != 2:
             raise TypeError("UniTensor.PutBlock", "[ERROR] the block must be a dense rank-2 UniTensor")
@@ -972,8 +980,8 @@ class UniTensor:
     def GetBlock(self, *qnum):
         """UniTensor.py:3062-3286: a COPY of the sector as an untagged rank-2 UniTensor."""
         if not self.is_symm:
-            if len(qnum):
-                raise TypeError("UniTensor.GetBlock", "[ERROR] Cannot get block with qnums from a non-symmetry tensor")
+            # UniTensor.py:3169-3195 (charges, if given, are ignored).  Always a copy here; the reference hands out
+            # a view of a contiguous Storage.  (Its is_diag branch cannot run: `self.Storage.bonds`, :3172.)
             if self.is_diag:
                 out = UniTensor(bonds=[Bond(self.bonds[0].dim), Bond(self.bonds[1].dim)], rowrank=1, check=False,
                                 is_diag=True)
@@ -981,8 +989,13 @@ class UniTensor:
                 return out
             x = self._contiguous_dense(self._dense)
             x = x.clone() if x is self._dense else x
+            n = int(x.numel())
+            if self.rowrank == 0 or len(self.bonds) - self.rowrank == 0:
+                out = UniTensor(bonds=[Bond(n)], rowrank=0 if self.rowrank == 0 else 1, check=False)
+                out._mac(torch_tensor=x.flatten())
+                return out
             r = int(np.prod([b.dim for b in self.bonds[:self.rowrank]], dtype=np.int64))
-            out = UniTensor(bonds=[Bond(r), Bond(max(1, x.numel() // max(r, 1)))], rowrank=1, check=False)
+            out = UniTensor(bonds=[Bond(r), Bond(n // r)], rowrank=1, check=False)
             out._mac(torch_tensor=x.reshape(r, -1))
             return out
         s = self._find_block(qnum, "UniTensor.GetBlock")
@@ -1082,6 +1095,8 @@ def _dense_gemm(A2, B2):
     """[M,K] x [K,N] on the family-3 kernel (single-problem group, cached per shape)."""
     M, K = A2.shape
     N = B2.shape[1]
+    if int(B2.shape[0]) != int(K):      # torch.matmul / tensordot of the reference raise RuntimeError here
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)" % (M, K, B2.shape[0], N))
     _lib.require_cuda_tensor(A2, "contraction")
     if B2.dtype != A2.dtype:
         raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (A2.dtype, B2.dtype))

@@ -16,8 +16,16 @@ from .UniTensor import Contract, UniTensor, _dense_gemm
 
 
 def _new_label(a):
-    """Smallest negative label of `a` (0 if none): new internal bonds get tmp-1, tmp-2 (linalg.py:535-539)."""
+    """Smallest negative label of `a` (0 if none): the new internal bonds of the symmetric SVD get tmp-1, tmp-2."""
     neg = a.labels[a.labels < 0]
+    return 0 if len(neg) == 0 else int(np.min(neg))
+
+
+def _new_label_ref(a):
+    """The reference's rule for the dense factorisations (linalg.py:363-367, :428-432, :535-539): the POSITION of the
+    first negative label (`np.min(np.argwhere(labels < 0))`, 0 if there is none), so the new bonds are labelled
+    -1 / -2 or 0 / -1 whatever the labels' values.  Kept as is: scripts relabel the factors anyway (iTEBD.py:118)."""
+    neg = np.argwhere(a.labels < 0)
     return 0 if len(neg) == 0 else int(np.min(neg))
 
 
@@ -150,7 +158,7 @@ def Qr(a):
         raise Exception("Qr(UniTensor)", "[ERROR] Qr can only accept UniTensor")
     _check_rank2(a, "Qr")
     q, r = torch.linalg.qr(a._dense)
-    tmp = _new_label(a)
+    tmp = _new_label_ref(a)
     tq = _rank2(q, labels=[a.labels[0], tmp - 1])
     tr = _rank2(r, labels=[tq.labels[1], a.labels[1]])
     return tq, tr
@@ -163,7 +171,7 @@ def Qdr(a):
     q, r = torch.linalg.qr(a._dense)
     d = r.diag()
     r = (r.t() / d).t()
-    tmp = _new_label(a)
+    tmp = _new_label_ref(a)
     tq = _rank2(q, labels=[a.labels[0], tmp - 1])
     td = _rank2(d, labels=[tmp - 1, tmp - 2], is_diag=True)
     tr = _rank2(r, labels=[td.labels[1], a.labels[1]])
@@ -179,7 +187,7 @@ def _svd(a, keepdim, who):
     x = a._dense
     drv = os.environ.get("TOR10_SVD_DRIVER") if x.device.type == "cuda" else None
     u, s, vh = torch.linalg.svd(x, full_matrices=False, driver=drv or None)
-    tmp = _new_label(a)
+    tmp = _new_label_ref(a)
     if keepdim is not None:
         if keepdim < 0 or keepdim > len(s):
             raise ValueError("Svd_truncate", "[ERROR] the keepdim=%d is invalid, must larger than 0 and smaller than "
@@ -290,6 +298,10 @@ def Matmul(a, b):
         raise Exception("Matmul(a,b)", "Matmul can only accept two regular Tensors")
     if not (len(a.labels) == 2 and len(b.labels) == 2 and a.rowrank == 1 and b.rowrank == 1):
         raise Exception("Matmul(a,b)", "Matmul can only accept two UniTensor with each has 1 inbond and 1 outbond")
+    if int(a.bonds[1].dim) != int(b.bonds[0].dim):
+        # the reference leaves this to torch.matmul (linalg.py:722-733), which raises RuntimeError
+        raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)"
+                           % (a.bonds[0].dim, a.bonds[1].dim, b.bonds[0].dim, b.bonds[1].dim))
     bonds = [a.bonds[0], b.bonds[1]]
     if a.is_diag and b.is_diag:
         return _rank2(a._dense * b._dense, bonds=bonds, is_diag=True)
