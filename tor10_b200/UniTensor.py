@@ -198,7 +198,8 @@ class UniTensor:
         """True when the arena is laid out for the CURRENT bond order and row/col split.  The reference only
         tracks the bond order (`_contiguous`, quirk Q1); here a changed rowrank also counts as "needs relayout"."""
         return (self._contiguous and self.rowrank == self._layout.rowrank
-                and np.array_equal(self._layout.braket, self.braket))     # tags exchanged (Whole_transpose): relayout
+                and self._layout.braket_key == np.asarray(self.braket, dtype=np.int64).tobytes())
+        # (last term: tags exchanged by Whole_transpose -> another sector table, relayout needed)
 
     def _logical_layout(self):
         return _plan.get_layout(list(self.bonds), self.braket, self.rowrank, self._arena.device)

@@ -69,6 +69,7 @@ class BlockLayout:
         self.nsym = int(bonds[0].nsym)
         self.dims = i64([b.dim for b in bonds])
         self.braket = i32(braket)
+        self.braket_key = np.asarray(braket, dtype=np.int64).tobytes()   # cheap equality test (UniTensor._layout_current)
         self.accu_in, self.accu_out = accu_offsets(self.dims, self.rowrank)
         self.R = int(np.prod(self.dims[:rowrank], dtype=np.int64))
         self.C = int(np.prod(self.dims[rowrank:], dtype=np.int64))
