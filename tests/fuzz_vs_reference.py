@@ -35,6 +35,8 @@ as shipped (compatibility shim of tests/golden/make_golden.py).  Random inputs, 
     python tests/fuzz_vs_reference.py q2     <seed> <cases>      symmetric Contract OUTSIDE the well-defined domain
                                                                  (random tags and row/column splits, quirk Q2): both
                                                                  libraries against a dense einsum of the densified operands
+    python tests/fuzz_vs_reference.py f32    <seed> <cases>      float32 symmetric tensors: Contract (1e-5), exact
+                                                                 relayout, dtype of the results, mixed-dtype operands
     python tests/fuzz_vs_reference.py linalg <seed> <cases>      + - * / between dense / diagonal tensors and scalars,
                                                                  Svd_truncate, Qr, Inverse, Det, Norm, ExpH, Abs, Mean,
                                                                  Otimes, Todense, Whole_transpose (metadata; values,
@@ -1293,6 +1295,70 @@ def fuzz_q2(argv):
     return stats.get("prod_differs_U1only", 0)
 
 
+def fuzz_f32(argv):
+    seed, ncase = int(argv[0]) if len(argv) > 0 else 1, int(argv[1]) if len(argv) > 1 else 300
+    rng = np.random.default_rng(seed)
+    stats, fails = {"contract": 0, "relayout": 0, "mixed_dtype": 0}, []
+    def rmk(spec, dtype):
+        t = ref.UniTensor(bonds=[G.mk_bond(b) for b in spec["bonds"]], rowrank=spec["rowrank"], labels=spec["labels"], dtype=dtype)
+        return t
+    for it in range(ncase):
+        syms = G.SYMSETS[int(rng.integers(0, len(G.SYMSETS)))]
+        nfa, nk, nfb = int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(1, 3))
+        A, B = G.wd_pair(rng, syms, nfa, nk, nfb, maxdim=4)
+        if not (G.need_ok(A, True, nfa) and G.need_ok(B, False, nfb)): continue
+        try:
+            ra, rb = rmk(A, torch.float32), rmk(B, torch.float32)
+            pa, pb = psym(T, A, seed=1 + it, device="cpu", dtype=torch.float32), psym(T, B, seed=900 + it, device="cpu", dtype=torch.float32)
+        except Exception:
+            continue
+        for i in range(len(ra.Storage)): ra.Storage[i] = pa.Storage[i].clone()
+        for i in range(len(rb.Storage)): rb.Storage[i] = pb.Storage[i].clone()
+        try:
+            rc = ref.Contract(ra, rb)
+        except Exception:
+            continue
+        try:
+            pc = T.Contract(pa, pb)
+        except Exception as e:
+            fails.append((it, "product raises %r" % (e,))); continue
+        stats["contract"] += 1
+        if pc.dtype != torch.float32 or any(x.dtype != torch.float32 for x in pc.Storage) or rc.Storage[0].dtype != torch.float32:
+            fails.append((it, "dtype %s / ref %s" % (pc.dtype, rc.Storage[0].dtype))); continue
+        for x, y in zip(rc.Storage, pc.Storage):
+            x, y = x.numpy().astype(np.float64), y.cpu().numpy().astype(np.float64)
+            if x.shape != y.shape or (x.size and np.abs(x - y).max() > 1e-5 * max(1.0, np.abs(x).max())):
+                fails.append((it, "values")); break
+        # Permute -> Contiguous keeps fp32 and is exact
+        n = len(A["bonds"]); perm = [int(x) for x in rng.permutation(n)]; rr = int(rng.integers(1, n))
+        if perm != list(range(n)) or rr == A["rowrank"]:
+            try:
+                ra.Permute(perm, rowrank=rr); rcn = ra.Contiguous()
+            except Exception:
+                rcn = None
+            if rcn is not None and sum(x.numel() for x in rcn.Storage) == sum(x.numel() for x in ra.Storage):
+                pa.Permute(perm, rowrank=rr); pcn = pa.Contiguous()
+                stats["relayout"] += 1
+                if any(x.dtype != torch.float32 for x in pcn.Storage):
+                    fails.append((it, "relayout dtype"))
+                elif not all(np.array_equal(x.numpy(), y.cpu().numpy()) for x, y in zip(rcn.Storage, pcn.Storage)):
+                    # may be quirk Q3 (negative-index writes) even with equal counts: check via fp64 oracle-free rule
+                    stats["relayout_values_diff"] = stats.get("relayout_values_diff", 0) + 1
+        # mixed dtype operands: what happens in each library
+        try:
+            pa64 = psym(T, A, seed=1 + it, device="cpu"); ra64 = G.fill(G.mk_tensor(A), 1 + it)
+            o = []
+            for fn in (lambda: ref.Contract(ra64, rb), lambda: T.Contract(pa64, pb)):
+                try: fn(); o.append("ok")
+                except Exception as e: o.append(type(e).__name__)
+            stats["mixed_dtype"] += 1
+            stats["mixed_" + o[0] + "_" + o[1]] = stats.get("mixed_" + o[0] + "_" + o[1], 0) + 1
+        except Exception:
+            pass
+    print("seed", seed, stats, "fails", len(fails), fails[:5])
+    return len(fails)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "sym"
-    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops, "ctor": fuzz_ctor, "symerr": fuzz_symerr, "denseapi": fuzz_denseapi, "q2": fuzz_q2}[mode](sys.argv[2:]) else 0)
+    sys.exit(1 if {"sym": fuzz_sym, "dense": fuzz_dense, "blocks": fuzz_blocks, "net": fuzz_net, "ops": fuzz_ops, "linalg": fuzz_linalg, "symops": fuzz_symops, "ctor": fuzz_ctor, "symerr": fuzz_symerr, "denseapi": fuzz_denseapi, "q2": fuzz_q2, "f32": fuzz_f32}[mode](sys.argv[2:]) else 0)
