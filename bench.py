@@ -122,6 +122,29 @@ def cpu_port_run(chi, budget_s, max_reps):
     return flops, times
 
 
+def oracle_parity(chi, c):
+    """Checker (not timed, not shipped): the oracle's Contract of the same seeded operands against the product's
+    result `c` -- block map bit-exact, every block within max|d| / max|ref| (fp64 bar: 1e-12)."""
+    import torch
+    from helpers import osym, rel_err
+    from oracle import tor10_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    A, B = c3a_specs(chi)
+    mm = lambda x, y: torch.matmul(torch.from_numpy(x), torch.from_numpy(y)).numpy()  # noqa: E731
+    oc = orc.contract_sym(osym(A, seed=1003), osym(B, seed=1004), matmul=mm)
+    maps_equal = bool(np.array_equal(c._block_qnums, oc.bm.block_qnums)
+                      and np.array_equal(c._Ket_mapper_blks, oc.bm.ket_map)
+                      and np.array_equal(c._Bra_mapper_blks, oc.bm.bra_map)
+                      and [tuple(x.shape) for x in c.Storage] == [tuple(x.shape) for x in oc.blocks])
+    worst = 0.0
+    if maps_equal:
+        for blk, ref in zip(c.Storage, oc.blocks):
+            worst = max(worst, rel_err(blk.cpu().numpy(), ref))
+    return {"maps_equal": maps_equal, "max_rel_err": worst if maps_equal else None, "tolerance": 1e-12,
+            "blocks": len(oc.blocks), "vs": "oracle.contract_sym (numpy restatement of UniTensor.py:2108-2129, "
+            ":3692-3743, pinned to the reference's fixtures) on the same seeded operands, full size"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,8 +191,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; the bench prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            # NCCL logs to stdout by default and the bench prints ONE JSON line there: keep the level the caller
+            # asked for and send the log (communicator / rank lines included) to stderr instead
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     import tor10_b200 as T
     from helpers import psym
@@ -393,6 +418,13 @@ def main():
         del a32, b32
     clocks = sampler.stop() if sampler is not None else None
 
+    # ---- parity of the headline result against the oracle (checker, outside every timed region) ----------
+    step()                       # at N > 1: the gathered result, as every rank sees it
+    torch.cuda.synchronize()
+    barrier()
+    parity = oracle_parity(args.chi, out_holder[0]) if rank == 0 else None
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -402,24 +434,26 @@ def main():
     import ctypes
     lib = T._lib.load()
     tf = ctypes.c_double(0.0)
-    T._lib.check(lib.t10_probe_f64_peak(1, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
-    dmma_probe = tf.value
-    T._lib.check(lib.t10_probe_f64_peak(0, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
-    dfma_probe = tf.value
+    # peak policy: three repetitions of every probe, the best of each is kept, all are printed; the denominator
+    # is never below the cuBLAS DGEMM figure
+    dmma_runs, dfma_runs, dgemm_runs = [], [], []
     n = 8192
     x = torch.rand((n, n), device=dev, dtype=torch.float64)
     y = torch.rand((n, n), device=dev, dtype=torch.float64)
     torch.matmul(x, y)
-    best = 1e9
     for _ in range(3):
+        T._lib.check(lib.t10_probe_f64_peak(1, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
+        dmma_runs.append(tf.value)
+        T._lib.check(lib.t10_probe_f64_peak(0, 4096, ctypes.byref(tf), T._lib.stream_ptr()))
+        dfma_runs.append(tf.value)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         torch.matmul(x, y)
         e.record()
         torch.cuda.synchronize()
-        best = min(best, s.elapsed_time(e))
-    dgemm_tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        dgemm_runs.append(2.0 * n ** 3 / (s.elapsed_time(e) * 1e-3) / 1e12)
     del x, y
+    dmma_probe, dfma_probe, dgemm_tf = max(dmma_runs), max(dfma_runs), max(dgemm_runs)
     peak_tf = max(dgemm_tf, dmma_probe)
 
     peaks = {}
@@ -474,9 +508,10 @@ def main():
                      "traffic": ({46: 61.82e6, 40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg)
                                  if (world == 1 and args.chi == 4096) else None),
                      "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
-                     "peak_source": "FP64 measured live in this run: max(torch.matmul f64 8192^3 = %.1f TF, DMMA "
-                                    "register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has no "
-                                    "fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe)},
+                     "peak_source": "FP64 measured live in this run, best of 3 each: max(torch.matmul f64 8192^3 = %.1f TF, "
+                                    "DMMA register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has "
+                                    "no fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe),
+                     "peak_runs": {"dmma_probe": dmma_runs, "dfma_probe": dfma_runs, "dgemm_8192": dgemm_runs}},
         "roofline_relayout": {"kernel": ("k_relayout_runs (block relayout replayed through the runs of its element index)"
                                          if (plan.rel_a is not None and plan.rel_a.d_runs is not None) else
                                          "k_relayout_index (block relayout replayed through its element index)"
@@ -489,6 +524,7 @@ def main():
                               # (profiles/r01_ncu_summary.md); the destination partly stays in L2
                               "traffic": RELAYOUT_TRAFFIC.get("runs" if (plan.rel_a is not None and plan.rel_a.d_runs is not None)
                                                               else "index") if (world == 1 and args.chi == 4096) else None},
+        "parity": parity,
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -260,6 +260,19 @@ def test_pickle_and_save_load_round_trip(T, tmp_path):
     r1, r2 = T.Contract(a, t2), T.Contract(c, t2)
     for x, y in zip(blocks_np(r1), blocks_np(r2)):
         assert np.array_equal(x, y)
+    # tensors whose ARENA layout differs from their logical split / tags: changed rowrank, exchanged tags
+    f = psym(T, A, seed=79, device=DEV)
+    f.SetRowRank(1)
+    f2 = pickle.loads(pickle.dumps(f))
+    assert f2.rowrank == 1 and f2.labels.tolist() == f.labels.tolist()
+    for x, y in zip(blocks_np(f.Contiguous()), blocks_np(f2.Contiguous())):
+        assert np.array_equal(x, y)
+    g = psym(T, A, seed=80, device=DEV).Whole_transpose()
+    g2 = pickle.loads(pickle.dumps(g))
+    assert g2.braket.tolist() == g.braket.tolist() and g2.rowrank == g.rowrank
+    assert np.array_equal(g2._block_qnums, g._block_qnums)
+    for x, y in zip(blocks_np(g.Contiguous()), blocks_np(g2.Contiguous())):
+        assert np.array_equal(x, y)
     # dense tensors too
     d = T.UniTensor(bonds=[T.Bond(3), T.Bond(4)], rowrank=1, device=torch.device(DEV))
     d.Storage = torch.arange(12, dtype=torch.float64).reshape(3, 4).to(DEV)

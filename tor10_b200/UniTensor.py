@@ -288,6 +288,10 @@ class UniTensor:
         if self.is_symm:
             d["_pickled_blocks"] = [x.detach().cpu() for x in self.Storage]
             d["_pickled_device"] = str(self._arena.device)
+            # the arena's layout can differ from the logical split / tags (SetRowRank, Permute(rowrank=...),
+            # Whole_transpose, Q2 results): the blocks above are the MEMORY layout's, so record that layout
+            d["_mem_rowrank"] = int(self._layout.rowrank)
+            d["_mem_braket"] = np.asarray(self._layout.braket, dtype=np.int64).tolist()
             for k in ("_arena", "_blocks", "_layout", "_bq"):
                 d.pop(k, None)
         return d
@@ -301,7 +305,10 @@ class UniTensor:
             # memory layout = bonds in memory order
             mem_bonds = [self.bonds[self._inv_mapper[i]] for i in range(len(self.bonds))]
             mem_braket = self.braket[self._inv_mapper]
-            rr = d.get("_mem_rowrank", self.rowrank)
+            rr = self.__dict__.pop("_mem_rowrank", self.rowrank)
+            mb = self.__dict__.pop("_mem_braket", None)
+            if mb is not None:
+                mem_braket = np.asarray(mb, dtype=np.int64)
             self._layout = _plan.get_layout(mem_bonds, mem_braket, rr, device)
             self._arena = self._layout.new_arena(blocks[0].dtype, zero=True)
             self._blocks, self._bq = None, None
@@ -1141,6 +1148,12 @@ def _dense_gemm(A2, B2):
 
 def _diag_scale(x, diag, axis):
     """x scaled along `axis` by the 1-D tensor `diag` (family-2 kernel t10_diag_scale); x is made contiguous."""
+    # torch.tensordot with the densified diagonal (UniTensor.py:3756-3765) raises RuntimeError on these
+    if int(x.shape[axis]) != int(diag.numel()):
+        raise RuntimeError("Contract(a,b): contracted dimensions need to match, but the tensor has size %d and the "
+                           "diagonal tensor has size %d" % (int(x.shape[axis]), int(diag.numel())))
+    if diag.dtype != x.dtype:
+        raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (x.dtype, diag.dtype))
     x = UniTensor._contiguous_dense(x)
     _lib.require_cuda_tensor(x, "contraction with a diagonal tensor")
     out = torch.empty_like(x)

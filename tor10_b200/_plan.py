@@ -19,9 +19,69 @@ import torch
 from . import _lib
 from ._lib import ARENA_ALIGN, RELAYOUT_TC, RELAYOUT_TR, check, i32, i64, np_ptr
 
-_LAYOUTS = {}
-_RELAYOUTS = {}
-_CONTRACTS = {}
+class LRU:
+    """Bounded plan cache: a dict with least-recently-used eviction on the number of entries and, when the
+    entries report `plan_bytes()`, on the bytes of device tables they keep alive.  An evicted plan's tensors
+    are released as soon as no other plan references them (a workload whose charge tables change every step --
+    a symmetric Svd_truncate producing a new bond per iTEBD / DMRG step -- would otherwise grow until OOM)."""
+
+    def __init__(self, max_entries, max_bytes=None):
+        import collections
+        self.d = collections.OrderedDict()
+        self.max_entries, self.max_bytes = int(max_entries), max_bytes
+        self.bytes = 0
+        self.evicted = 0
+
+    @staticmethod
+    def _nbytes(v):
+        f = getattr(v, "plan_bytes", None)
+        return int(f()) if f is not None else 0
+
+    def get(self, key, default=None):
+        v = self.d.get(key)
+        if v is None:
+            return default
+        self.d.move_to_end(key)
+        return v
+
+    def __setitem__(self, key, v):
+        old = self.d.pop(key, None)
+        if old is not None:
+            self.bytes -= self._nbytes(old)
+        self.d[key] = v
+        self.bytes += self._nbytes(v)
+        while len(self.d) > 1 and (len(self.d) > self.max_entries
+                                   or (self.max_bytes is not None and self.bytes > self.max_bytes)):
+            _, ev = self.d.popitem(last=False)
+            self.bytes -= self._nbytes(ev)
+            self.evicted += 1
+
+    def recount(self):
+        """Plan memory can grow after insertion (the element index is built on first use)."""
+        self.bytes = sum(self._nbytes(v) for v in self.d.values())
+
+    def __len__(self):
+        return len(self.d)
+
+    def __contains__(self, key):
+        return key in self.d
+
+    def items(self):
+        return self.d.items()
+
+    def values(self):
+        return self.d.values()
+
+    def clear(self):
+        self.d.clear()
+        self.bytes = 0
+
+
+_CACHE_ENTRIES = int(os.environ.get("TOR10_PLAN_CACHE_ENTRIES", "512"))
+_CACHE_BYTES = int(os.environ.get("TOR10_PLAN_CACHE_MB", "4096")) << 20
+_LAYOUTS = LRU(_CACHE_ENTRIES, _CACHE_BYTES)
+_RELAYOUTS = LRU(_CACHE_ENTRIES, _CACHE_BYTES)
+_CONTRACTS = LRU(_CACHE_ENTRIES, _CACHE_BYTES)
 STATS = {"layout_build": 0, "relayout_build": 0, "contract_build": 0}
 
 
@@ -33,6 +93,14 @@ def clear_caches():
     mod = sys.modules.get(__package__ + ".UniTensor")
     if mod is not None:
         mod._GEMM_GROUPS.clear()
+    par = sys.modules.get(__package__ + ".parallel")
+    if par is not None:
+        par._SYMM.clear()
+        par._STAGE.clear()
+
+
+def _tensor_bytes(*ts):
+    return sum(int(t.numel()) * t.element_size() for t in ts if t is not None)
 
 
 def _dev_index(device):
@@ -142,6 +210,10 @@ class BlockLayout:
 
     def sector_of(self, qnum):
         return self._qindex.get(tuple(int(x) for x in qnum))
+
+    def plan_bytes(self):
+        return _tensor_bytes(self.d_block_qnums, self.d_ket_map, self.d_bra_map, self.d_ket_idx, self.d_bra_idx,
+                             self.d_sec_info, self.d_rowbase, self.d_coloff)
 
     def new_arena(self, dtype, zero=True):
         n = self.arena_elems + ARENA_ALIGN
@@ -264,6 +336,10 @@ class RelayoutPlan:
 
     INDEX_BUDGET_BYTES = int(os.environ.get("TOR10_RELAYOUT_INDEX_MB", "1024")) << 20
 
+    def plan_bytes(self):
+        return _tensor_bytes(self.RR, self.RC, self.CR, self.CC, self.d_tiles, self.d_index, self.d_runs,
+                             getattr(self, "d_chunk_first", None))
+
     def _build_index(self):
         """Element index of the relayout (plan time): the block kernel in EMIT mode."""
         n = (self.packed.size + 1) // 2 * 2
@@ -313,9 +389,16 @@ class RelayoutPlan:
 
     def run(self, src_arena, dst):
         """dst must hold packed.size elements; padding/unmatched space is left untouched."""
-        if self.use_index and self.d_index is None and self.ntiles and src_arena.numel() < 2 ** 31:
-            with torch.cuda.device(self.L.device):
-                self._build_index()
+        if self.use_index and self.d_index is None and self.d_runs is None and self.ntiles \
+                and src_arena.numel() < 2 ** 31:
+            # an index over its memory budget is only built (transiently) when its run-length form was asked for;
+            # otherwise such a plan replays through the factored tables, which need no plan memory at all
+            if self.index_fits or os.environ.get("TOR10_RELAYOUT_RUNS", "auto") == "1":
+                with torch.cuda.device(self.L.device):
+                    self._build_index()
+                _RELAYOUTS.recount()
+            else:
+                self.use_index = False
         if self.d_runs is not None and dst.numel() >= self.index_n and dst.data_ptr() % 16 == 0:
             check(_lib.load().t10_relayout_runs(_lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(),
                                                 self.index_n, self.d_runs.data_ptr(), self.nruns,
