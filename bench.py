@@ -494,7 +494,9 @@ def main():
         "fp32_contract": fp32_info,
         "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
                                           + 1 + ((1 if plan._transport in ("fused", "p2p") else 0) if world > 1 else 0))),
-        "roofline": {"kernel": ("k_ggemm_f64_mixed_sk (grouped DMMA GEMM, mixed tile shapes, stream-K)"
+        "roofline": {"kernel": ("k_ggemm_f64_tma (grouped DMMA GEMM, TMA producer warp + mbarrier ring, mixed tile "
+                                "shapes, stream-K)" if getattr(plan.gemm, "tma", False) else
+                                "k_ggemm_f64_mixed_sk (grouped DMMA GEMM, mixed tile shapes, stream-K)"
                                 if getattr(plan.gemm, "streamk", False) else
                                 "k_ggemm_f64_mixed (grouped DMMA GEMM, mixed tile shapes)" if plan.gemm.tile_cfg == 46 else
                                 "k_ggemm_f64_v5 (grouped DMMA GEMM, aligned software-pipelined kernel)"
@@ -505,14 +507,18 @@ def main():
                      # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 49.97 MB + 4.21 MB (tile_cfg 40),
                      # 50.00 MB + 3.02 MB (tile_cfg 3)
                      # 50.74 MB + 11.09 MB (tile_cfg 46 as stream-K: the parked partial tiles add ~8 MB)
-                     "traffic": ({46: 61.82e6, 40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg)
+                     "traffic": (None if getattr(plan.gemm, "tma", False) else
+                                 {46: 61.82e6, 40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg)
                                  if (world == 1 and args.chi == 4096) else None),
                      "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
                      "peak_source": "FP64 measured live in this run, best of 3 each: max(torch.matmul f64 8192^3 = %.1f TF, "
                                     "DMMA register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has "
                                     "no fp64 entry" % (dgemm_tf, dmma_probe, dfma_probe),
                      "peak_runs": {"dmma_probe": dmma_runs, "dfma_probe": dfma_runs, "dgemm_8192": dgemm_runs}},
-        "roofline_relayout": {"kernel": ("k_relayout_runs (block relayout replayed through the runs of its element index)"
+        "roofline_relayout": {"kernel": ("k_relayout_segments (block relayout replayed through the contiguous segments "
+                                         "of its element index, one warp per segment)"
+                                         if (plan.rel_a is not None and plan.rel_a.d_seg is not None) else
+                                         "k_relayout_runs (block relayout replayed through the runs of its element index)"
                                          if (plan.rel_a is not None and plan.rel_a.d_runs is not None) else
                                          "k_relayout_index (block relayout replayed through its element index)"
                                          if (plan.rel_a is not None and plan.rel_a.d_index is not None) else
@@ -522,8 +528,9 @@ def main():
                               "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src,
                               # dram read+write of one launch, ncu --set full at chi=4096 on 1 GPU
                               # (profiles/r01_ncu_summary.md); the destination partly stays in L2
-                              "traffic": RELAYOUT_TRAFFIC.get("runs" if (plan.rel_a is not None and plan.rel_a.d_runs is not None)
-                                                              else "index") if (world == 1 and args.chi == 4096) else None},
+                              "traffic": (None if (plan.rel_a is not None and plan.rel_a.d_seg is not None) else
+                                          RELAYOUT_TRAFFIC.get("runs" if (plan.rel_a is not None and plan.rel_a.d_runs is not None)
+                                                               else "index")) if (world == 1 and args.chi == 4096) else None},
         "parity": parity,
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }

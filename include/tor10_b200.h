@@ -151,6 +151,17 @@ int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int64_t n, con
 int t10_relayout_runs(int dtype, const void* d_src, void* d_dst, int64_t n, const int32_t* d_runs,
                       int64_t nruns, const int32_t* d_chunk_first, t10_stream_t stream);
 
+/* Replay of a relayout through SEGMENTS of its element index: maximal pieces contiguous on both sides, cut at
+ * T10_RELAYOUT_SEG_MAX elements.  d_seg: int32 quadruples {dst_start, src_start, len, source} (16-byte aligned);
+ * the piece is read from arena h_src[source] (nsrc <= 8 base pointers: this GPU's arena, and in sector-resident
+ * multi-GPU runs the NVLink peer mappings of the other ranks' arenas -- the relayout of a sharded tensor fetches
+ * what it needs from its owners inside the copy, without a collective).  src_start < 0: zero fill.  One warp per
+ * segment; elements no segment covers are left untouched.  Opens the programmatic launch window of the kernel
+ * that follows on the stream (t10_ggemm_tma with pdl = 1).                                            */
+#define T10_RELAYOUT_SEG_MAX 256
+int t10_relayout_segments(int dtype, int nsrc, const void* const* h_src, void* d_dst, int64_t nseg,
+                          const int32_t* d_seg, t10_stream_t stream);
+
 /* Multi-GPU sector gather over NVLink peer memory (no reference counterpart: the reference has no
  * multi-device code).  dst[lo_i .. hi_i) = src_i[lo_i .. hi_i) for nseg <= 16 slices, where src_i are
  * peer-mapped (symmetric-memory) staging buffers of the other ranks; bounds multiples of 16 bytes.
@@ -236,6 +247,24 @@ int t10_ggemm_streamk_allgather(const void* d_A, const void* d_B, int npeers, in
                                 const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
                                 const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch,
                                 t10_stream_t stream);
+
+/* TMA-fed form of t10_ggemm_streamk (tile_cfg 47; same tables, same results bit for bit): a producer warp feeds
+ * the four DMMA warps of a CTA through `cp.async.bulk.tensor` boxes and full/empty mbarriers, the ring of stages is
+ * carried across pieces, sector edges and the K tail are zero-filled by the TMA unit.  Needs one tensor map per
+ * sector and operand: t10_ggemm_tma_encode (HOST call, no launch) writes 2 * nprob maps of 128 bytes into h_maps
+ * -- map 2i describes A of problem i (k x m, row pitch lda), map 2i + 1 its B (n x k, row pitch ldb) -- for the
+ * operand base pointers d_A / d_B; the caller copies them to 64-byte aligned device memory (d_maps) and may reuse
+ * them for as long as the operands keep their addresses.  Every lda / ldb / a_off / b_off must be even and the base
+ * pointers 16-byte aligned.  pdl != 0 launches with programmatic stream serialisation: the kernel's set-up overlaps
+ * the tail of the preceding kernel on the stream (the block relayout that writes A) and its first operand load
+ * waits for that kernel's completion (griddepcontrol.wait).
+ * t10_ggemm_tma_slots: co-resident CTAs of the kernel (the largest legal nslots).                             */
+int t10_ggemm_tma_slots(int* nslots);
+int t10_ggemm_tma_encode(int64_t nprob, const t10_gemm_problem* h_prob, const void* d_A, const void* d_B,
+                         void* h_maps);
+int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
+                  const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
+                  void* d_ws, int32_t* d_flags, int32_t epoch, int pdl, t10_stream_t stream);
 
 /* Deterministic second half of a split-K product: d_out[i] = sum_{s < nslices} d_ws[s * n + i], added in slice
  * order.  A GEMM whose output is a handful of tiles but whose K is long (the norms and expectation values of

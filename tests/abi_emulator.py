@@ -150,6 +150,24 @@ class Emu:
         return 0
     def t10_ggemm_streamk(self, A, B, Cc, nprob, prob, npieces, tiles, pieces, nslots, slots, ws, flags, epoch, st):
         return self.t10_ggemm(0, 46, A, B, Cc, nprob, prob, npieces, tiles, nslots, slots, None, st)
+    def t10_relayout_segments(self, dt, nsrc, hsrc, dst, nseg, seg, st):
+        fd = np.float64 if dt == 0 else np.float32
+        sg = arr(seg, nseg * 4, np.int32).reshape(nseg, 4)
+        bases = [int(x or 0) for x in hsrc]
+        isz = np.dtype(fd).itemsize
+        for d, s_, ln, w in sg.tolist():
+            o = arr(dst + d * isz, ln, fd)
+            o[:] = 0 if s_ < 0 else arr(bases[w] + s_ * isz, ln, fd)
+        return 0
+    def t10_ggemm_tma_slots(self, out):
+        out._obj.value = 296
+        return 0
+    def t10_ggemm_tma_encode(self, nprob, prob, A, B, hmaps):
+        arr(hmaps, 2, np.int64)[:] = [A or 0, B or 0]       # the emulated "maps" are just the operand bases
+        return 0
+    def t10_ggemm_tma(self, maps, Cc, nprob, prob, npieces, tiles, pieces, nslots, slots, ws, flags, epoch, pdl, st):
+        A, B = (int(x) for x in arr(maps, 2, np.int64))
+        return self.t10_ggemm(0, 46, A, B, Cc, nprob, prob, npieces, tiles, nslots, slots, None, st)
     def t10_ggemm_slots(self, dt, cfg, out):
         out._obj.value = 296
         return 0

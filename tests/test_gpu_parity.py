@@ -189,11 +189,13 @@ def test_relayout_vs_oracle_medium(T):
         assert np.array_equal(x, y)
 
 
-@pytest.mark.parametrize("mode", ["runs", "index", "blocks"])
+@pytest.mark.parametrize("mode", ["segments", "runs", "index", "blocks"])
 def test_relayout_replay_modes(T, mode, monkeypatch):
-    """The three replays of one relayout -- runs of the element index (default when runs are long), the
-    element index, the factored block kernel -- move exactly the same bits (oracle: vectorised restatement
-    of UniTensor.py:2108-2129).  Narrow charge range = long runs (degeneracies of 40-80)."""
+    """The four replays of one relayout -- segments of the element index (one warp per contiguous piece: default
+    when the pieces are long), its runs with bisection, the element index itself, the factored block kernel --
+    move exactly the same bits (oracle: vectorised restatement of UniTensor.py:2108-2129).  Narrow charge range =
+    long runs (degeneracies of 40-80)."""
+    monkeypatch.setenv("TOR10_RELAYOUT_MODE", "auto" if mode == "segments" else "index")
     monkeypatch.setenv("TOR10_RELAYOUT_RUNS", "1" if mode == "runs" else "auto")
     monkeypatch.setenv("TOR10_RELAYOUT_INDEX", "0" if mode == "blocks" else "1")
     T._plan.clear_caches()
@@ -208,6 +210,7 @@ def test_relayout_replay_modes(T, mode, monkeypatch):
     a, b = psym(T, A, seed=31, device=DEV), psym(T, B, seed=32, device=DEV)
     Cc = T.Contract(a, b)
     pl = T._plan.get_contract_plan(a, b)
+    assert (pl.rel_a.d_seg is not None) == (mode == "segments")
     assert (pl.rel_a.d_runs is not None) == (mode == "runs")
     assert (pl.rel_a.d_index is not None) == (mode == "index")
     oc = orc.contract_sym(osym(A, seed=31), osym(B, seed=32))
@@ -340,18 +343,22 @@ def test_dense_contract_split_k(T, shape):
     assert rel_err(got.cpu().numpy(), want) <= TOL64
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("chi", [640, 1000])
-def test_contract_stream_k_forced(T, chi, monkeypatch):
+def test_contract_stream_k_forced(T, chi, tma, monkeypatch):
     """Stream-K forced on small groups: shares of a few k-steps, so tiles are cut into MANY pieces (several parked
-    partials per tile, added in slot order).  Same result as the oracle within 1e-12 and bit-reproducible."""
+    partials per tile, added in slot order).  Same result as the oracle within 1e-12 and bit-reproducible -- on the
+    TMA-fed kernel (ggemm_tma.cu, default) and on the cp.async kernel it replaces (TOR10_GGEMM_TMA=0)."""
     monkeypatch.setenv("TOR10_GGEMM_CFG", "46")
     monkeypatch.setenv("TOR10_GGEMM_STREAMK", "force")
+    monkeypatch.setenv("TOR10_GGEMM_TMA", tma)
     T._plan.clear_caches()
     A, B = _c3_spec(chi, -3, 3, 1.5)
     a, b = psym(T, A, seed=21, device=DEV), psym(T, B, seed=22, device=DEV)
     c1 = T.Contract(a, b)
     plan = T._plan.get_contract_plan(a, b)
-    assert plan.gemm.tile_cfg == 46 and plan.gemm.streamk and plan.gemm.sk_parked > 0
+    assert plan.gemm.tile_cfg == 46 and plan.gemm.sk_parked > 0
+    assert plan.gemm.tma == (tma == "1") and plan.gemm.streamk == (tma == "0")
     c2 = T.Contract(a, b)
     oc = orc.contract_sym(osym(A, seed=21), osym(B, seed=22))
     for x, y, ref in zip(blocks_np(c1), blocks_np(c2), oc.blocks):

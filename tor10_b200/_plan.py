@@ -325,6 +325,7 @@ class RelayoutPlan:
             torch.zeros(32, dtype=torch.uint8, device=dev)
         self.d_index = None
         self.d_runs = None
+        self.d_seg, self.nseg = None, 0
         self.index_n = 0
         # replay form: element index (fastest: 16.4 us cold / 8.4 us L2-warm on the C3a operand), runs of the
         # index (18.4 / 12.4 us, ~1 % of the index's memory: taken when the index exceeds its budget, or with
@@ -337,7 +338,7 @@ class RelayoutPlan:
     INDEX_BUDGET_BYTES = int(os.environ.get("TOR10_RELAYOUT_INDEX_MB", "1024")) << 20
 
     def plan_bytes(self):
-        return _tensor_bytes(self.RR, self.RC, self.CR, self.CC, self.d_tiles, self.d_index, self.d_runs,
+        return _tensor_bytes(self.RR, self.RC, self.CR, self.CC, self.d_tiles, self.d_index, self.d_runs, self.d_seg,
                              getattr(self, "d_chunk_first", None))
 
     def _build_index(self):
@@ -350,9 +351,56 @@ class RelayoutPlan:
             self.CR.data_ptr(), self.CC.data_ptr(), self.M.d_rowbase.data_ptr(), self.M.d_coloff.data_ptr(),
             self.M.d_ket_map.data_ptr() if self.check else None, self.M.d_bra_map.data_ptr() if self.check else None,
             self.d_index.data_ptr(), _lib.stream_ptr()))
-        self._build_runs()
+        self._build_segments()
+        if self.d_seg is None:
+            self._build_runs()
 
     RUN_CHUNK = 1024      # RR_CHUNK of relayout.cu
+    SEG_MAX = 256         # T10_RELAYOUT_SEG_MAX
+
+    def _build_segments(self):
+        """Segment form of the element index (plan time, torch ops on the device, 32 M elements at a time):
+        maximal pieces contiguous on both sides, cut at SEG_MAX elements, as int32 {dst, src, len, source}.
+        Taken when the pieces average at least 16 elements (TOR10_RELAYOUT_MODE=segments: always); the element
+        index is then dropped."""
+        self.d_seg, self.nseg = None, 0
+        mode = os.environ.get("TOR10_RELAYOUT_MODE", "auto")
+        if mode not in ("auto", "segments") or os.environ.get("TOR10_RELAYOUT_RUNS", "auto") == "1":
+            return
+        n = self.index_n
+        dev = self.d_index.device
+        parts = []
+        CH = 1 << 25
+        for c0 in range(0, n, CH):
+            idx = self.d_index[c0:min(n, c0 + CH)].to(torch.int64)
+            m = idx.numel()
+            pos = torch.arange(c0, c0 + m, device=dev, dtype=torch.int64)
+            key = torch.where(idx >= 0, idx - pos, idx - (1 << 40))
+            brk = torch.ones(m, dtype=torch.bool, device=dev)
+            brk[1:] = key[1:] != key[:-1]
+            st = torch.nonzero(brk).flatten()
+            ln = torch.diff(st, append=torch.tensor([m], device=dev, dtype=torch.int64))
+            src = idx[st]
+            keep = src != -2                                  # untouched destination (padding, foreign sectors)
+            st, ln, src = st[keep] + c0, ln[keep], src[keep]
+            npc = (ln + self.SEG_MAX - 1) // self.SEG_MAX     # pieces per run
+            rep = torch.repeat_interleave(torch.arange(st.numel(), device=dev), npc)
+            first = torch.cumsum(npc, 0) - npc
+            k = torch.arange(rep.numel(), device=dev) - first[rep]
+            off = k * self.SEG_MAX
+            seg = torch.empty((rep.numel(), 4), dtype=torch.int32, device=dev)
+            seg[:, 0] = (st[rep] + off).to(torch.int32)
+            seg[:, 1] = torch.where(src[rep] >= 0, src[rep] + off, src[rep]).to(torch.int32)
+            seg[:, 2] = torch.minimum(ln[rep] - off, torch.tensor(self.SEG_MAX, device=dev)).to(torch.int32)
+            seg[:, 3] = 0
+            parts.append(seg)
+        seg = torch.cat(parts) if len(parts) > 1 else parts[0]
+        nseg = int(seg.shape[0])
+        if nseg == 0 or (mode == "auto" and self.moved_elems < 16 * nseg):
+            return
+        self.d_seg, self.nseg = seg.contiguous(), nseg
+        self.d_index = None                    # 4 B per element of plan memory given back
+        self.use_index = False
 
     def _build_runs(self):
         """Run-length form of the element index (plan time, torch ops on the device): maximal pieces with
@@ -387,9 +435,17 @@ class RelayoutPlan:
         self.d_index = None                    # 4 B per element of plan memory given back
         self.use_index = False
 
+    def run_segments(self, src_ptrs, dst, dcode, seg=None, nseg=None):
+        """Segment replay; src_ptrs[k] = base pointer of source arena k (one entry on a single GPU)."""
+        arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+        seg = self.d_seg if seg is None else seg
+        check(_lib.load().t10_relayout_segments(dcode, len(src_ptrs), arr, dst.data_ptr(),
+                                                self.nseg if nseg is None else nseg, seg.data_ptr(),
+                                                _lib.stream_ptr()))
+
     def run(self, src_arena, dst):
         """dst must hold packed.size elements; padding/unmatched space is left untouched."""
-        if self.use_index and self.d_index is None and self.d_runs is None and self.ntiles \
+        if self.use_index and self.d_index is None and self.d_runs is None and self.d_seg is None and self.ntiles \
                 and src_arena.numel() < 2 ** 31:
             # an index over its memory budget is only built (transiently) when its run-length form was asked for;
             # otherwise such a plan replays through the factored tables, which need no plan memory at all
@@ -399,6 +455,9 @@ class RelayoutPlan:
                 _RELAYOUTS.recount()
             else:
                 self.use_index = False
+        if self.d_seg is not None and dst.numel() >= self.index_n:
+            self.run_segments([src_arena.data_ptr()], dst, _lib.dtype_code(src_arena.dtype))
+            return dst
         if self.d_runs is not None and dst.numel() >= self.index_n and dst.data_ptr() % 16 == 0:
             check(_lib.load().t10_relayout_runs(_lib.dtype_code(src_arena.dtype), src_arena.data_ptr(), dst.data_ptr(),
                                                 self.index_n, self.d_runs.data_ptr(), self.nruns,
@@ -547,7 +606,19 @@ class GemmGroup:
         self.d_prob = torch.from_numpy(self.problems.view(np.uint8).reshape(-1)).to(device) if self.nprob else \
             torch.zeros(48, dtype=torch.uint8, device=device)
         self.streamk = False
-        if (dtype == torch.float64 and self.tile_cfg == 46 and self.ntiles > 0
+        self.tma = False
+        self._tma_maps = {}
+        if (dtype == torch.float64 and self.tile_cfg in (46, 40) and self.ntiles > 0 and self.aligned
+                and not sharded and os.environ.get("TOR10_GGEMM_TMA", "1") == "1"):
+            # TMA-fed kernel (ggemm_tma.cu): stream-K pieces when there is enough work to cut, whole tiles in LPT
+            # slots otherwise -- one kernel, one table format
+            nres = C.c_int(0)
+            with torch.cuda.device(device):
+                check(lib.t10_ggemm_tma_slots(C.byref(nres)))
+            self.tma = self.build_streamk(int(nres.value), phases=1, min_ksteps=int(os.environ.get("TOR10_TMA_MINK", "4")),
+                                          fixed_default=float(os.environ.get("TOR10_TMA_FIXED", "1"))) \
+                or self.build_whole_tiles(int(nres.value))
+        if (not self.tma and dtype == torch.float64 and self.tile_cfg == 46 and self.ntiles > 0
                 and os.environ.get("TOR10_GGEMM_STREAMK", "1") in ("1", "force")):
             # a sharded rank pushes its tiles to the peers as they finish: two groups of tiles, so that half of them
             # finish (and travel) while the other half computes
@@ -564,7 +635,36 @@ class GemmGroup:
                                for p in self.problems))
 
     # ---- stream-K on the mixed-shape kernel: balance k-steps, not tiles -------------------------------------
-    def build_streamk(self, nslots, phases=1):
+    def build_whole_tiles(self, nslots):
+        """Whole tiles (mixed shapes) dealt to CTA slots by LPT, in the piece-table format of the stream-K / TMA
+        kernels: every piece is a complete tile (no parked partials)."""
+        lib = _lib.load()
+        nt = C.c_int64(0)
+        check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), 0, 0, None, None, C.byref(nt)))
+        if nt.value == 0:
+            return False
+        nslots = max(1, min(int(nslots), int(nt.value)))
+        tl = np.zeros((nt.value, 4), dtype=np.int32)
+        slots = np.zeros(nslots + 1, dtype=np.int32)
+        check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), nslots, nt.value, np_ptr(tl),
+                                       np_ptr(slots), C.byref(nt)))
+        kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
+        pcs = np.zeros((len(tl), 4), dtype=np.int32)
+        pcs[:, 1] = kts
+        pcs[:, 2] = -1
+        dev = self.d_prob.device
+        self.sk_phases, self.sk_parked = 1, 0
+        self.sk_nslots, self.sk_npieces = nslots, len(tl)
+        self.d_sk_tiles = torch.from_numpy(tl).to(dev)
+        self.d_sk_pieces = torch.from_numpy(pcs).to(dev)
+        self.d_sk_slots = torch.from_numpy(slots).to(dev)
+        self.d_sk_ws = torch.empty(128 * 34, dtype=torch.float64, device=dev)
+        self.d_sk_flags = torch.zeros(nslots + 1, dtype=torch.int32, device=dev)
+        self.sk_epoch = 0
+        self._sk_static = None
+        return True
+
+    def build_streamk(self, nslots, phases=1, min_ksteps=16, fixed_default=2.0):
         """Cut the tile list (t10_ggemm_plan_tiles, cfg 46, heaviest first) into `nslots` equal shares of k-steps
         (a k-step of the aligned kernel costs the same whatever the tile's raggedness; +2 per piece for the
         pipeline fill).  A tile cut across CTAs becomes pieces: the CTAs holding its leading k-ranges park partial
@@ -577,7 +677,7 @@ class GemmGroup:
             return False
         tl = np.zeros((nt.value, 4), dtype=np.int32)
         check(lib.t10_ggemm_plan_tiles(46, self.nprob, np_ptr(self.problems), 0, nt.value, np_ptr(tl), None, C.byref(nt)))
-        fixed = float(os.environ.get("TOR10_SK_FIXED", "2"))          # measured on C3a: (2, 2) 109.9 us, (3, 2) 110.9,
+        fixed = float(os.environ.get("TOR10_SK_FIXED", str(fixed_default)))   # measured on C3a: (2, 2) 109.9 us, (3, 2) 110.9,
         min_piece = int(os.environ.get("TOR10_SK_MINPIECE", "2"))     # (2, 1) 109.7, (2, 4) 111.5, (5, 2) 111.9, (2, 8) 120.1
         if os.environ.get("TOR10_SK_ORDER", "cost") == "spread":
             # low-discrepancy interleaving of the cost-sorted list: every CTA's share then mixes long and short
@@ -585,7 +685,7 @@ class GemmGroup:
             key = (np.arange(len(tl)) * 0.6180339887498949) % 1.0
             tl = tl[np.argsort(key, kind="stable")]
         kts = (self.problems["k"][tl[:, 0]].astype(np.int64) + 15) // 16
-        if int(kts.sum()) < 16 * nslots and os.environ.get("TOR10_GGEMM_STREAMK") != "force":
+        if int(kts.sum()) < min_ksteps * nslots and os.environ.get("TOR10_GGEMM_STREAMK") != "force":
             return False          # too little work per CTA to be worth cutting tiles (plain LPT slots instead)
         # PHASES (sharded ranks with the fused all-gather): the tiles are dealt into `phases` groups of equal work and
         # every group is cut into nslots shares of its own, run one group after the other.  With one group all CTAs
@@ -678,6 +778,27 @@ class GemmGroup:
         check(st[0](A.data_ptr(), B.data_ptr(), Cc.data_ptr(), self.nprob, st[1], self.sk_npieces, st[2], st[3],
                     self.sk_nslots, st[4], st[5], st[6], self.sk_epoch, _lib.stream_ptr()))
 
+    def run_tma(self, A, B, Cc, pdl=False):
+        """TMA-fed kernel: the tensor maps (one per sector and operand) are encoded on the host for the operands'
+        base addresses and cached -- a loop that contracts the same tensors, or whose scratch buffers come back from
+        the caching allocator at the same address, pays for them once."""
+        lib = _lib.load()
+        key = (A.data_ptr(), B.data_ptr())
+        d_maps = self._tma_maps.get(key)
+        if d_maps is None:
+            h = torch.empty(max(self.nprob, 1) * 256, dtype=torch.uint8,
+                            pin_memory=(A.device.type == "cuda"))
+            check(lib.t10_ggemm_tma_encode(self.nprob, np_ptr(self.problems), A.data_ptr(), B.data_ptr(), h.data_ptr()))
+            d_maps = h.to(A.device, non_blocking=True)
+            if len(self._tma_maps) >= 16:
+                self._tma_maps.pop(next(iter(self._tma_maps)))
+            self._tma_maps[key] = d_maps
+        self.sk_epoch = self.sk_epoch % 2000000000 + 1
+        check(lib.t10_ggemm_tma(d_maps.data_ptr(), Cc.data_ptr(), self.nprob, self.d_prob.data_ptr(), self.sk_npieces,
+                                self.d_sk_tiles.data_ptr(), self.d_sk_pieces.data_ptr(), self.sk_nslots,
+                                self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(), self.d_sk_flags.data_ptr(),
+                                self.sk_epoch, 1 if pdl else 0, _lib.stream_ptr()))
+
     def fusable(self):
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
         return self.dtype_code == _lib.dtype_code(torch.float64) and self.tile_cfg in FUSABLE_CFGS
@@ -701,7 +822,9 @@ class GemmGroup:
                                               self.d_sched.data_ptr() if self.d_sched is not None else None,
                                               _lib.stream_ptr()))
 
-    def run(self, A, B, Cc):
+    def run(self, A, B, Cc, pdl=False):
+        if self.tma:
+            return self.run_tma(A, B, Cc, pdl=pdl)
         if self.streamk:
             return self.run_streamk(A, B, Cc)
         check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
@@ -712,6 +835,7 @@ class GemmGroup:
 
 
 _PLAN_SERIAL = itertools.count()
+_PDL = os.environ.get("TOR10_PDL", "1") == "1"
 
 
 class ContractPlan:
@@ -857,7 +981,8 @@ class ContractPlan:
                     if self._transport == "nccl":
                         parallel.gather_ranges(Cc, self.ranges, self.shard[0])
             else:
-                self.gemm.run(A, B, Cc)
+                # the GEMM's set-up overlaps the tail of the relayout that precedes it (programmatic dependent launch)
+                self.gemm.run(A, B, Cc, pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL)
         out = UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.mem_rowrank, self.Lo, Cc)
         if self.out_rowrank != self.mem_rowrank:
             out.rowrank = self.out_rowrank

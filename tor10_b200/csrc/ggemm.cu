@@ -1013,6 +1013,7 @@ using CfgS = F64Cfg<32, 32, 16, 16, 3>;       // tile_cfg 8: 32x32 tiles, 4 warp
 using CfgL = F64Cfg<64, 128, 32, 64, 3>;      // tile_cfg 42: cuBLAS's large-GEMM shape, 128 thr, 82.9 KB
 
 static unsigned long long* g_trace = nullptr;   // t10_ggemm_set_trace
+unsigned long long* ggemm_trace_ptr() { return g_trace; }   // ggemm_tma.cu
 
 // launch == false: only report the number of resident CTA slots (sm_count x CTAs/SM)
 template <class Cfg, int MIN_CTAS, bool RAGGED = true>
