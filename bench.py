@@ -200,8 +200,9 @@ def main():
     from helpers import psym
     from tor10_b200 import _plan, parallel
 
+    default_transport = os.environ.get("TOR10_GATHER", "auto")
     if world > 1:
-        parallel.enable(transport=os.environ.get("TOR10_GATHER", "auto"))
+        parallel.enable(transport=default_transport)
     A, B = c3a_specs(args.chi)
     a = psym(T, A, seed=1003, device=dev)
     b = psym(T, B, seed=1004, device=dev)
@@ -256,18 +257,33 @@ def main():
     ms_per_step = ms_total / args.steps
     value = flops / (ms_per_step * 1e-3) / 1e9
 
-    # ---- the same step with results left sharded (every rank keeps only its own sectors: no collective) ----
-    sharded_ms = None
+    # ---- the same step through the other transports: "pull" / "fused" gather the result on every rank --------
+    others = {}
     if world > 1:
-        parallel.enable(transport="none")
-        for _ in range(3):
-            step()
-        barrier()
-        ts = float(np.sum(timed_loop(step, args.steps)))
-        tt = torch.tensor([ts], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        sharded_ms = float(tt.item()) / args.steps
-        parallel.enable(transport=os.environ.get("TOR10_GATHER", "auto"))
+        for tr in ("resident", "pull", "fused"):
+            if tr == plan._transport:
+                continue
+            try:
+                parallel.enable(transport=tr)
+                for _ in range(3):
+                    step()
+                barrier()
+                ts = float(np.sum(timed_loop(step, args.steps)))
+                tt = torch.tensor([ts], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item()) / args.steps
+                step()
+                c_tr = out_holder[0]
+                c_tr._materialize()
+                torch.cuda.synchronize()
+                barrier()
+                others[tr] = {"ms_per_step": ms, "value": flops / (ms * 1e-3) / 1e9,
+                              "parity": oracle_parity(args.chi, c_tr) if rank == 0 else None}
+                barrier()
+            except Exception as exc:   # a transport that cannot run here is reported, not hidden
+                others[tr] = {"error": repr(exc)[:300]}
+        out_holder[0] = None
+        parallel.enable(transport=default_transport)
         plan = _plan.get_contract_plan(a, b)
 
     # ---- stage timings on this rank's share (roofline of the dominant kernel) ---------------
@@ -304,6 +320,12 @@ def main():
         """Arena ranges of the operand this rank's share of the contraction reads."""
         if rel is None:
             secs = direct_sectors
+        elif rel.d_seg is not None:
+            sg = rel.d_seg.cpu().numpy().astype(np.int64)
+            sg = sg[sg[:, 1] >= 0]
+            first, last = sg[:, 1], sg[:, 1] + sg[:, 2] - 1
+            secs = np.unique(np.concatenate([np.searchsorted(layout.arena_off, first, side="right") - 1,
+                                             np.searchsorted(layout.arena_off, last, side="right") - 1]))
         elif rel.d_runs is not None:
             rr = rel.d_runs.cpu().numpy().astype(np.int64)
             ln = np.diff(rr[:, 0])
@@ -339,7 +361,7 @@ def main():
             b._arena[lo:hi].copy_(hB[lo:hi], non_blocking=True)
         c = T.Contract(a, b)
         for lo, hi in out_c:
-            hC[lo:hi].copy_(c._arena[lo:hi], non_blocking=True)
+            hC[lo:hi].copy_(c._arena[lo:hi], non_blocking=True)     # (this rank's own sectors when sharded)
 
     for _ in range(3):
         e2e_step()
@@ -419,7 +441,9 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- parity of the headline result against the oracle (checker, outside every timed region) ----------
-    step()                       # at N > 1: the gathered result, as every rank sees it
+    step()
+    if world > 1:
+        out_holder[0]._materialize()      # sector-resident result: gathered on demand, on every rank
     torch.cuda.synchronize()
     barrier()
     parity = oracle_parity(args.chi, out_holder[0]) if rank == 0 else None
@@ -472,15 +496,18 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "sectors": int(plan.Lo.nsec), "algorithmic_gflop": flops / 1e9,
                    "nnz_per_operand": int(a._layout.nnz), "tile_cfg": plan.gemm.tile_cfg,
-                   "parallelism": ("sectors sharded over %d GPUs (%s); result gathered on every rank: %s" % (
-                       world, "LPT by flops" if plan._transport in ("fused", "none") else "contiguous runs balanced by flops",
-                       {"fused": "all-gather fused into the GEMM epilogue (every output tile stored into all ranks' "
-                                 "symmetric staging arenas over NVLink peer memory, system-scope flags, one wait+copy "
-                                 "kernel)",
-                        "p2p": "symmetric-memory staging + device barrier + one pull kernel over NVLink peer memory",
+                   "parallelism": ("sectors sharded over %d GPUs, LPT by flops; transport %s: %s" % (
+                       world, plan._transport,
+                       {"resident": "results stay sector-resident (every rank keeps the sectors it computed, owner table "
+                                    "on the tensor, later contractions read them in place or fetch foreign sectors over "
+                                    "NVLink peer memory, gathered on demand); no collective on the data path",
+                        "pull": "resident, then every rank pulls the other ranks' sectors over NVLink peer memory",
+                        "fused": "all-gather fused into the GEMM epilogue (tiles stored into all ranks' symmetric "
+                                 "staging arenas over NVLink, system-scope flags, one wait+copy kernel)",
+                        "p2p": "symmetric-memory staging + device barrier + one pull kernel",
                         "nccl": "NCCL all_gather_into_tensor"}.get(plan._transport, str(plan._transport))))
                    if world > 1 else "1 GPU",
-                   "value_if_result_stays_sharded_gflops": (flops / (sharded_ms * 1e-3) / 1e9) if sharded_ms else None,
+                   "other_transports": others if world > 1 else None,
                    "l2": "flushed between steps (256 MiB write); every step timed by its own CUDA event pair",
                    "plan": "cached (block maps, relayout tables, tile table built once outside the timed region)"},
         "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
@@ -493,7 +520,7 @@ def main():
                             "downloads its own output sectors" if world > 1 else "Whole operands in, whole result out"))},
         "fp32_contract": fp32_info,
         "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
-                                          + 1 + ((1 if plan._transport in ("fused", "p2p") else 0) if world > 1 else 0))),
+                                          + 1 + ((1 if plan._transport in ("fused", "p2p", "pull") else 0) if world > 1 else 0))),
         "roofline": {"kernel": ("k_ggemm_f64_tma (grouped DMMA GEMM, TMA producer warp + mbarrier ring, mixed tile "
                                 "shapes, stream-K)" if getattr(plan.gemm, "tma", False) else
                                 "k_ggemm_f64_mixed_sk (grouped DMMA GEMM, mixed tile shapes, stream-K)"

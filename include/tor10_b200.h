@@ -264,7 +264,24 @@ int t10_ggemm_tma_encode(int64_t nprob, const t10_gemm_problem* h_prob, const vo
                          void* h_maps);
 int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
                   const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
-                  void* d_ws, int32_t* d_flags, int32_t epoch, int pdl, t10_stream_t stream);
+                  void* d_ws, int32_t* d_flags, int32_t epoch, int pdl,
+                  int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr, t10_stream_t stream);
+
+/* Progress words of sector-resident multi-GPU runs (no reference counterpart: the reference is single-device).
+ * Every rank keeps ONE uint64 progress word in symmetric memory: the number of resident operations it has
+ * completed.  t10_ggemm_tma with nsig > 0: the last CTA of the launch stores `sig_value` into h_sig_flags[0..nsig)
+ * (normally just this rank's own word: a local store) with system-scope release semantics (d_done_ctr:
+ * zero-initialised int32 arrival counter, reset by the kernel).  t10_signal_flags does the same from a one-warp
+ * kernel (after operations that only READ peer memory).
+ * t10_wait_flags: a one-warp kernel that acquires *h_flags[i] >= h_need[i], i < n <= 8, before anything launched
+ * after it on the stream runs; h_flags[i] is a rank's progress word, a peer's through its NVLink mapping (the READER
+ * polls remotely: a producer nobody waits for never touches the link).  Placed before a kernel that reads sectors
+ * another rank produced, or that overwrites memory other ranks may still be reading.  timeout_ms > 0 bounds the
+ * wait: on expiry *d_err is set to 1 + i and the kernel TRAPS (the CUDA context fails loudly; nothing downstream
+ * consumes missing data); timeout_ms = 0 waits for ever, like NCCL.                                        */
+int t10_signal_flags(int nsig, void* const* h_sig_flags, uint64_t value, t10_stream_t stream);
+int t10_wait_flags(int n, const void* const* h_flags, const uint64_t* h_need, int64_t timeout_ms, int32_t* d_err,
+                   t10_stream_t stream);
 
 /* Deterministic second half of a split-K product: d_out[i] = sum_{s < nslices} d_ws[s * n + i], added in slice
  * order.  A GEMM whose output is a handful of tiles but whose K is long (the norms and expectation values of

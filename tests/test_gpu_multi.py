@@ -106,7 +106,75 @@ def _worker_streamk(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker, _worker_streamk], ids=["transports", "streamk_allgather"])
+def _worker_resident(rank, world, port, q):
+    """Sector-resident chaining: Contract -> Contract -> Contract with results that are never gathered.
+    c = a.b stays resident; c.e reads c IN PLACE (ownership inherited from c's row sectors); relabelled c needs a
+    RELAYOUT whose foreign pieces are read from the owner's arena over NVLink; x.c reads resident c as the SECOND
+    operand (foreign sectors pulled).  Ten rounds wrap the ring of result arenas (write-after-read protocol).
+    Everything is compared with the same chain on one GPU (rounding level) and, first link, with the oracle."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import tor10_b200 as T
+    from tor10_b200 import parallel
+    from helpers import osym, psym, rel_err
+    from oracle import tor10_oracle as orc
+    from test_gpu_parity import _c3_spec
+    dev = "cuda:%d" % rank
+    chi = 160
+    A, B = _c3_spec(chi, -7, 6, 2.5)
+    a, b = psym(T, A, seed=41, device=dev), psym(T, B, seed=42, device=dev)
+    E = dict(B, labels=[4, 5, 6, 7])
+    e = psym(T, E, seed=43, device=dev)
+    vb, pb = B["bonds"][1], B["bonds"][0]                      # (chi KET), (p KET)
+    E3 = {"bonds": [vb, pb, B["bonds"][2], B["bonds"][3]], "rowrank": 2, "labels": [4, 5, 6, 7]}
+    e3 = psym(T, E3, seed=44, device=dev)
+    A2 = {"bonds": [A["bonds"][0], A["bonds"][2], A["bonds"][3], A["bonds"][1]], "rowrank": 2, "labels": [8, 9, 0, 1]}
+    a2 = psym(T, A2, seed=45, device=dev)
+    why, err = [], 0.0
+
+    def chain():
+        c = T.Contract(a, b)                                   # labels [0, 1, 4, 5]
+        d = T.Contract(c, e)                                   # c in place, ownership inherited
+        c3 = T.Contract(a, b)
+        c3.SetLabels([0, 1, 5, 4])
+        f = T.Contract(c3, e3)                                 # relayout of a resident operand
+        g = T.Contract(a2, c)                                  # resident SECOND operand: foreign sectors pulled
+        return c, d, f, g
+
+    ref = [[x.clone() for x in t.Storage] for t in chain()]
+    oc = orc.contract_sym(osym(A, seed=41), osym(B, seed=42))
+    for tr in ("resident", "pull"):
+        parallel.enable(transport=tr)
+        for it in range(10):
+            c, d, f, g = chain()
+            if it == 0:
+                if c._res is None or d._res is None or f._res is None or g._res is None:
+                    why.append("%s: results are not resident" % tr)
+                elif tr == "resident":
+                    if c._res.valid.all() and world > 1:
+                        why.append("resident: every sector is local (nothing was sharded)")
+                    pl = T._plan.get_contract_plan(c, e)
+                    if not getattr(pl, "inherited", False):
+                        why.append("resident: ownership was not inherited from the resident operand")
+            if it in (0, 9):
+                got = [[x.clone() for x in t.Storage] for t in (c, d, f, g)]   # gathers on demand (every rank)
+                for gt, rf in zip(got, ref):
+                    for x, y in zip(gt, rf):
+                        den = float(y.abs().max())
+                        err = max(err, float((x - y).abs().max()) / (den if den > 0 else 1.0))
+                if it == 0:
+                    err = max(err, max(rel_err(x.cpu().numpy(), y) for x, y in zip(got[0], oc.blocks)))
+        parallel.disable()
+        T._plan.clear_caches()
+    torch.cuda.synchronize()
+    q.put((rank, "; ".join(why), err))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_worker, _worker_streamk, _worker_resident],
+                         ids=["transports", "streamk_allgather", "resident_chain"])
 def test_sharded_contract_two_gpus(worker):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -117,7 +185,7 @@ def test_sharded_contract_two_gpus(worker):
     procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

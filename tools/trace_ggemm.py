@@ -20,7 +20,7 @@ g = plan.gemm
 for _ in range(3):
     T.Contract(a, b)
 torch.cuda.synchronize()
-sk = getattr(g, "streamk", False)
+sk = getattr(g, "streamk", False) or getattr(g, "tma", False)
 ntl = g.sk_npieces if sk else g.ntiles
 trace = torch.zeros((ntl, 4), dtype=torch.int64, device=dev)
 lib = _lib.load()

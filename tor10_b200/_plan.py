@@ -97,6 +97,8 @@ def clear_caches():
     if par is not None:
         par._SYMM.clear()
         par._STAGE.clear()
+        if par._RES["world"] is not None:
+            par._RES["world"].pools.clear()
 
 
 def _tensor_bytes(*ts):
@@ -553,8 +555,10 @@ FALLBACK_CFG = 3
 class GemmGroup:
     """Problem table + tile table on the device."""
 
-    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True, sharded=False):
+    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True, sharded=False, resident=False):
         lib = _lib.load()
+        if resident:
+            sharded = False       # a rank's share of a resident contraction is an ordinary group: no fused push
         self.problems = np.ascontiguousarray(problems, dtype=_lib.GEMM_PROBLEM_DTYPE)
         self.nprob = len(self.problems)
         self.dtype_code = _lib.dtype_code(dtype)
@@ -778,7 +782,7 @@ class GemmGroup:
         check(st[0](A.data_ptr(), B.data_ptr(), Cc.data_ptr(), self.nprob, st[1], self.sk_npieces, st[2], st[3],
                     self.sk_nslots, st[4], st[5], st[6], self.sk_epoch, _lib.stream_ptr()))
 
-    def run_tma(self, A, B, Cc, pdl=False):
+    def run_tma(self, A, B, Cc, pdl=False, signal=None):
         """TMA-fed kernel: the tensor maps (one per sector and operand) are encoded on the host for the operands'
         base addresses and cached -- a loop that contracts the same tensors, or whose scratch buffers come back from
         the caching allocator at the same address, pays for them once."""
@@ -794,10 +798,12 @@ class GemmGroup:
                 self._tma_maps.pop(next(iter(self._tma_maps)))
             self._tma_maps[key] = d_maps
         self.sk_epoch = self.sk_epoch % 2000000000 + 1
+        nsig, sig_ptrs, sig_val, done = (0, None, 0, None) if signal is None else \
+            (len(signal[0]), signal[0], int(signal[1]), signal[2].data_ptr())
         check(lib.t10_ggemm_tma(d_maps.data_ptr(), Cc.data_ptr(), self.nprob, self.d_prob.data_ptr(), self.sk_npieces,
                                 self.d_sk_tiles.data_ptr(), self.d_sk_pieces.data_ptr(), self.sk_nslots,
                                 self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(), self.d_sk_flags.data_ptr(),
-                                self.sk_epoch, 1 if pdl else 0, _lib.stream_ptr()))
+                                self.sk_epoch, 1 if pdl else 0, nsig, sig_ptrs, sig_val, done, _lib.stream_ptr()))
 
     def fusable(self):
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
@@ -822,9 +828,15 @@ class GemmGroup:
                                               self.d_sched.data_ptr() if self.d_sched is not None else None,
                                               _lib.stream_ptr()))
 
-    def run(self, A, B, Cc, pdl=False):
+    def run(self, A, B, Cc, pdl=False, signal=None):
+        """signal = (ctypes array of progress-word addresses, value, arrival counter): published when the launch
+        has stored its last tile (sector-resident multi-GPU runs)."""
         if self.tma:
-            return self.run_tma(A, B, Cc, pdl=pdl)
+            return self.run_tma(A, B, Cc, pdl=pdl, signal=signal)
+        if signal is not None:
+            self.run(A, B, Cc)
+            check(_lib.load().t10_signal_flags(len(signal[0]), signal[0], int(signal[1]), _lib.stream_ptr()))
+            return
         if self.streamk:
             return self.run_streamk(A, B, Cc)
         check(_lib.load().t10_ggemm(self.dtype_code, self.tile_cfg, A.data_ptr(), B.data_ptr(), Cc.data_ptr(),
@@ -919,17 +931,27 @@ class ContractPlan:
             self.sector_bounds = bounds
             self.ranges = arena_ranges(Lo, bounds)
             owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(Lo.nsec), side="right")
-            if self._transport == "none" or (self._transport == "fused" and a.dtype == torch.float64
+            self.inherited = False
+            if self._transport in ("resident", "pull") and a._res is not None and ident_a \
+                    and a._res.world == world:
+                # ownership propagates: output sector q lives where A's row sector q lives, so a chain
+                # of contractions reads its running operand in place on every rank
+                from .parallel import inherit_owner
+                owner = inherit_owner(a._res.owner, matched, Lo.nsec, cost, world)
+                self.inherited = True
+            elif self._transport in ("none", "resident", "pull") or (self._transport == "fused" and a.dtype == torch.float64
                                              and pick_tile_cfg(None) in FUSABLE_CFGS):
                 # the fused GEMM -> all-gather stores tiles, not arena slices (and sharded results are not gathered
                 # at all): ownership need not be contiguous, so the sectors are balanced by LPT (the contiguous
                 # split of C3a at 2 ranks is 44 / 56 %)
                 owner = partition_lpt(cost, world)
             self.sector_owner = owner
+            self._own_valid = (np.asarray(owner) == rank) | (np.asarray(owner) < 0)
             matched = [m for m in matched if owner[m[0]] == rank]
         self.matched = matched
         sec_a = sorted(set(m[1] for m in matched))
         sec_b = sorted(set(m[2] for m in matched))
+        self.sec_a, self.sec_b = sec_a, sec_b
         # (stored sectors have an even leading dimension, so an operand read in place is always 16-byte aligned)
         self.rel_a = None if ident_a else get_relayout(Ma, La, map_a, padded=True, sectors=sec_a)
         self.rel_b = None if ident_b else get_relayout(Mb, Lb, map_b, padded=True, sectors=sec_b)
@@ -939,7 +961,9 @@ class ContractPlan:
         for i, (ob, ab, bb) in enumerate(matched):
             prob[i] = (pa.off[ab], pb.off[bb], Lo.arena_off[ob], La.rows[ab], Lb.cols[bb], La.cols[ab],
                        pa.ld[ab], pb.ld[bb], Lo.ld[ob])
-        self.gemm = GemmGroup(prob, dev, a.dtype, sharded=shard is not None and shard[1] > 1)
+        self.gemm = GemmGroup(prob, dev, a.dtype, sharded=shard is not None and shard[1] > 1,
+                              resident=self._transport in ("resident", "pull", "none"))
+        self._res_segs = {}
         self.flops = self.gemm.flops
         self.gemm_bytes = self.gemm.bytes
 
@@ -949,9 +973,12 @@ class ContractPlan:
         if b.dtype != dt:
             raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (dt, b.dtype))
         with _lib.on_device(a.device):
-            A = a._arena_tensor()
-            B = b._arena_tensor()
+            res_ok = self.shard is not None and self.shard[1] > 1 and self._transport in ("resident", "pull")
+            A = a._arena_tensor(resident_ok=res_ok)
+            B = b._arena_tensor(resident_ok=res_ok)
             sharded = self.shard is not None and self.shard[1] > 1
+            if sharded and self._transport in ("resident", "pull"):
+                return self._run_resident(a, b)
             fused = sharded and self._transport == "fused" and self.gemm.fusable()
             need_zero = (not self.all_matched) or (self.shard is not None and self._transport == "none")
             # every buffer is allocated before the first launch, so that the GEMM launch follows the ~10 us
@@ -983,12 +1010,117 @@ class ContractPlan:
             else:
                 # the GEMM's set-up overlaps the tail of the relayout that precedes it (programmatic dependent launch)
                 self.gemm.run(A, B, Cc, pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL)
-        out = UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.mem_rowrank, self.Lo, Cc)
+        return self._make_out(Cc)
+
+
+def _resident_segments(plan, which, rel, t):
+    """Segment table of relayout `rel` for a RESIDENT source tensor: the `source` column picks, per piece, the arena
+    it is read from -- 0 = this rank's, k > 0 = the NVLink peer mapping of the k-th foreign owner.  Cached per
+    (owner, valid) state of the operand.  Returns (table, foreign owners) or None when the plan has no segments."""
+    if rel.d_seg is None:
+        return None
+    res = t._res
+    key = (which, res.owner.tobytes(), res.valid.tobytes())
+    hit = plan._res_segs.get(key)
+    if hit is None:
+        M = rel.M
+        seg = rel.d_seg.clone()
+        src = seg[:, 1].to(torch.int64)
+        off = torch.from_numpy(np.asarray(M.arena_off, dtype=np.int64)).to(seg.device)
+        sec = torch.clamp(torch.searchsorted(off, src, right=True) - 1, min=0)
+        owner = torch.from_numpy(np.where(res.valid, -1, res.owner)).to(seg.device)[sec]      # -1: read locally
+        owner = torch.where(src >= 0, owner, torch.full_like(owner, -1))
+        foreign = sorted(int(x) for x in torch.unique(owner).tolist() if x >= 0)
+        col = torch.zeros_like(owner)
+        for k, o in enumerate(foreign):
+            col[owner == o] = k + 1
+        seg[:, 3] = col.to(torch.int32)
+        hit = (seg.contiguous(), foreign)
+        if len(plan._res_segs) > 8:
+            plan._res_segs.pop(next(iter(plan._res_segs)))
+        plan._res_segs[key] = hit
+    return hit
+
+
+def _run_resident(self, a, b):
+    """Sector-resident Contract (parallel transport "resident" / "pull"): this rank relayouts and multiplies only
+    the sectors it owns and keeps them; nothing is gathered ("pull": every rank then pulls the others' sectors
+    into its own arena over NVLink -- a gathered result without a staging copy).  See parallel.py."""
+    import weakref
+    from . import parallel
+    from .UniTensor import UniTensor
+    dt = a.dtype
+    rank, world = self.shard
+    rw = parallel.resident_world(a.device)
+    seq = rw.next_seq()
+    A = a._arena_tensor(resident_ok=True)
+    B = b._arena_tensor(resident_ok=True)
+    need = [0] * world
+    rel_args = {}
+    for which, t, rel, secs in (("a", a, self.rel_a, self.sec_a), ("b", b, self.rel_b, self.sec_b)):
+        res = t._res
+        if res is None:
+            continue
+        if res.slot is not None:
+            res.slot.last_read = max(res.slot.last_read, seq)
+        if rel is None:
+            parallel.pull_sectors(t, secs)              # read in place: foreign sectors come once, then stay
+            continue
+        if rel.d_seg is None and rel.use_index and rel.d_index is None:
+            rel._build_index()                          # (first use of the plan)
+        hit = _resident_segments(self, which, rel, t)
+        if hit is None or len(hit[1]) > 7:
+            parallel.pull_sectors(t, range(len(res.owner)))    # no segment form: bring the whole tensor here
+            continue
+        for o in hit[1]:
+            need[o] = max(need[o], res.seq)
+        rel_args[which] = hit
+    pool = rw.pool((self.serial, "out"), self.Lo.arena_elems + ARENA_ALIGN, dt, a.device)
+    slot, war = pool.acquire()
+    need = [max(n, war) if r != rank else 0 for r, n in enumerate(need)]
+    rw.wait(need)
+    Ap = torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt) if self.rel_a is not None else None
+    Bp = torch.empty(self.rel_b.packed.size, device=B.device, dtype=dt) if self.rel_b is not None else None
+    for which, t, rel, src, dst in (("a", a, self.rel_a, A, Ap), ("b", b, self.rel_b, B, Bp)):
+        if rel is None:
+            continue
+        hit = rel_args.get(which)
+        if hit is None:
+            rel.run(src, dst)
+        else:
+            ptrs = [src.data_ptr()] + [t._res.slot.peer_ptr(o) for o in hit[1]]
+            rel.run_segments(ptrs, dst, _lib.dtype_code(dt), seg=hit[0], nseg=int(hit[0].shape[0]))
+    Cc = slot.tensor()
+    self.gemm.run(Ap if Ap is not None else A, Bp if Bp is not None else B, Cc,
+                  pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL,
+                  signal=(rw.sig_ptrs, seq, rw.done_ctr))
+    out = self._make_out(Cc)
+    out._res = parallel.Residency(world, rank, self.sector_owner, seq, slot, self._own_valid)
+    slot.holder = weakref.ref(out)
+    if self._transport == "pull":
+        parallel.pull_sectors(out, range(self.Lo.nsec))
+    return out
+
+
+def _make_out(self, Cc):
+    """The result tensor around arena Cc (metadata replayed from a template built on the plan's first run)."""
+    from .UniTensor import UniTensor
+    tpl = self._out_tpl
+    if tpl is None:
+        tpl = UniTensor._from_plan(self.out_bonds, self.out_labels, self.out_braket, self.mem_rowrank, self.Lo, None)
         if self.out_rowrank != self.mem_rowrank:
-            out.rowrank = self.out_rowrank
-            out._bq = None
-            out._check_braket()
-        return out
+            tpl.rowrank = self.out_rowrank
+            tpl._bq = None
+            tpl._check_braket()
+        self._out_tpl = tpl
+    return UniTensor._from_template(tpl, Cc)
+
+
+ContractPlan._make_out = _make_out
+ContractPlan._out_tpl = None
+
+
+ContractPlan._run_resident = _run_resident
 
 
 def contract_key(a, b):
@@ -1000,7 +1132,10 @@ def contract_key(a, b):
 def get_contract_plan(a, b):
     from . import parallel
     shard = parallel.current_shard()
-    key = (contract_key(a, b), shard, parallel._STATE["transport"] if shard else None)
+    rk = None
+    if shard and a._res is not None and parallel._STATE["transport"] in ("resident", "pull"):
+        rk = a._res.key()          # ownership may propagate from a resident first operand
+    key = (contract_key(a, b), shard, parallel._STATE["transport"] if shard else None, rk)
     pl = _CONTRACTS.get(key)
     if pl is None:
         pl = ContractPlan(a, b, shard)

@@ -29,13 +29,12 @@
 
 namespace t10 {
 
-constexpr int TG_STAGES = 4;
 constexpr int TG_ABOX_ROWS = 32, TG_ABOX_COLS = 20;      // A box: 32 rows x (16 + 4) k
 constexpr int TG_BBOX_ROWS = 16, TG_BBOX_COLS = 36;      // B box: 16 k x (32 + 4) columns
 constexpr int TG_ABOX = TG_ABOX_ROWS * TG_ABOX_COLS * 8;   // 5120 B
 constexpr int TG_BBOX = TG_BBOX_ROWS * TG_BBOX_COLS * 8;   // 4608 B
 constexpr int TG_STAGE_BYTES = 4 * TG_ABOX + TG_BBOX;      // 25088 B: the largest shape (128x32)
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 128;   // + slack to align the ring to 128 B
+constexpr int tg_smem_bytes(int stages) { return stages * TG_STAGE_BYTES + 128; }   // + slack to align the ring
 constexpr int TG_THREADS = 160;                          // 4 DMMA warps + 1 producer warp
 static_assert(TG_ABOX % 128 == 0 && TG_BBOX % 128 == 0 && TG_STAGE_BYTES % 128 == 0, "TMA destinations: 128 B");
 static_assert(2 * TG_ABOX + 2 * TG_BBOX <= TG_STAGE_BYTES && TG_ABOX + 4 * TG_BBOX <= TG_STAGE_BYTES, "");
@@ -80,12 +79,26 @@ __device__ __forceinline__ void tg_consumer_sync() { asm volatile("bar.sync 1, 1
 __device__ __forceinline__ int tg_na(int shape) { return shape == 0 ? 2 : shape == 1 ? 1 : 4; }
 __device__ __forceinline__ int tg_nb(int shape) { return shape == 0 ? 2 : shape == 1 ? 4 : 1; }
 
-__global__ void __launch_bounds__(TG_THREADS, 2)
+// <4 stages, 2 CTAs per SM> (default: two DMMA warps per SM sub-partition) or <3 stages, 3 CTAs per SM, 128
+// registers> (three warps per sub-partition: more cover for each warp's LDS / epilogue phases, more pieces)
+// Completion signal of a sector-resident multi-GPU run: when the last CTA of the launch has stored its tiles it
+// raises this rank's progress word on every rank (its own included; peers through their NVLink mappings) to
+// `value` with system-scope release semantics.  Consumers on any rank acquire it before they read this rank's
+// sectors, and this rank's later launches acquire the peers' words before they overwrite memory the peers read.
+struct TgSignal {
+  int n;
+  unsigned long long* flag[8];
+  unsigned long long value;
+  int* done_ctr;                   // zero-initialised arrival counter of this launch (reset on exit)
+};
+
+template <int TG_STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(TG_THREADS, MIN_CTAS)
 k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase,
                 const t10_gemm_problem* __restrict__ prob, const int4* __restrict__ tiles,
                 const int4* __restrict__ pieces, const int32_t* __restrict__ slot_start,
                 double* __restrict__ sk_ws, int* __restrict__ sk_flags, int sk_epoch, int pdl,
-                unsigned long long* __restrict__ trace) {
+                unsigned long long* __restrict__ trace, const __grid_constant__ TgSignal sig) {
   extern __shared__ unsigned char tg_raw[];
   __shared__ __align__(8) unsigned long long bars[2 * TG_STAGES];
   unsigned char* ring = tg_raw + ((128u - (tg_smem(tg_raw) & 127u)) & 127u);   // (keeps the shared address space)
@@ -273,6 +286,55 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
       }
     }
   }
+  if (sig.n > 0) {
+    tg_consumer_sync();              // every DMMA warp's tile stores precede thread 0's fence
+    if (threadIdx.x == 0) {
+      __threadfence();               // release this CTA's tile stores before the arrival ...
+      if (atomicAdd(sig.done_ctr, 1) == (int)gridDim.x - 1) {
+        *sig.done_ctr = 0;
+        __threadfence();             // ... acquire everybody's; the system-scope release below is cumulative over them
+        for (int q = 0; q < sig.n; ++q)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sig.flag[q]), "l"(sig.value) : "memory");
+      }
+    }
+  }
+}
+
+__global__ void k_tg_signal(const __grid_constant__ TgSignal sig) {
+  if ((int)threadIdx.x < sig.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sig.flag[threadIdx.x]), "l"(sig.value) : "memory");
+  }
+}
+
+// Acquire: *flag[i] >= need[i] for i < n (flag[i]: a rank's progress word -- this GPU's own, or a peer's through its
+// NVLink mapping: the reader polls remotely, so a producer that nobody waits for never touches the link).
+// Bounded: after `timeout_ns` (0 = wait for ever, like NCCL) the kernel reports through *err and TRAPS -- the
+// context dies loudly instead of letting later kernels read sectors that never arrived.
+struct TgWait {
+  int n;
+  const unsigned long long* flag[8];
+  unsigned long long need[8];
+  unsigned long long timeout_ns;
+  int* err;
+};
+__global__ void k_tg_wait(const __grid_constant__ TgWait w) {
+  const int i = threadIdx.x;
+  if (i >= w.n) return;
+  unsigned long long t0, now, v = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flag[i]) : "memory");
+    if (v >= w.need[i]) break;
+    __nanosleep(100);
+    if (w.timeout_ns) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > w.timeout_ns) {
+        if (w.err) { *w.err = 1 + i; __threadfence_system(); }
+        asm volatile("trap;");
+      }
+    }
+  }
 }
 
 typedef CUresult (*TgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -299,15 +361,29 @@ extern unsigned long long* ggemm_trace_ptr();   // ggemm.cu (t10_ggemm_set_trace
 
 using namespace t10;
 
+static int tg_variant() {   // CTAs per SM: TOR10_TMA_CTAS=2 (default) | 3
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("TOR10_TMA_CTAS");
+    v = (e && atoi(e) == 3) ? 3 : 2;
+  }
+  return v;
+}
+
 extern "C" int t10_ggemm_tma_slots(int* nslots) {
   int dev = 0;
   T10_CUDA(cudaGetDevice(&dev));
   static int resident[64] = {0};
   T10_REQUIRE(dev >= 0 && dev < 64, T10_ERR_UNSUPPORTED, "device ordinal %d", dev);
   if (resident[dev] == 0) {
-    T10_CUDA(cudaFuncSetAttribute(k_ggemm_f64_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
     int occ = 0;
-    T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ggemm_f64_tma, TG_THREADS, TG_SMEM_BYTES));
+    if (tg_variant() == 3) {
+      T10_CUDA(cudaFuncSetAttribute(k_ggemm_f64_tma<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(3)));
+      T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ggemm_f64_tma<3, 3>, TG_THREADS, tg_smem_bytes(3)));
+    } else {
+      T10_CUDA(cudaFuncSetAttribute(k_ggemm_f64_tma<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem_bytes(4)));
+      T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ggemm_f64_tma<4, 2>, TG_THREADS, tg_smem_bytes(4)));
+    }
     T10_REQUIRE(occ >= 1, T10_ERR_CUDA, "TMA ggemm kernel does not fit on an SM");
     resident[dev] = occ * sm_count();
   }
@@ -347,11 +423,63 @@ extern "C" int t10_ggemm_tma_encode(int64_t nprob, const t10_gemm_problem* h_pro
   return T10_OK;
 }
 
+static int tg_fill_signal(TgSignal* sig, int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr) {
+  memset(sig, 0, sizeof(*sig));
+  T10_REQUIRE(nsig >= 0 && nsig <= 8, T10_ERR_INVALID, "signal: at most 8 ranks");
+  T10_REQUIRE(nsig == 0 || (h_sig_flags && d_done_ctr), T10_ERR_INVALID, "signal: flags need an arrival counter");
+  sig->n = nsig;
+  sig->value = sig_value;
+  sig->done_ctr = d_done_ctr;
+  for (int i = 0; i < nsig; ++i) sig->flag[i] = (unsigned long long*)h_sig_flags[i];
+  return T10_OK;
+}
+
+extern "C" int t10_signal_flags(int nsig, void* const* h_sig_flags, uint64_t value, t10_stream_t stream) {
+  TgSignal sig;
+  int dummy = 0;
+  int rc = tg_fill_signal(&sig, nsig, h_sig_flags, value, &dummy);
+  if (rc != T10_OK) return rc;
+  if (nsig == 0) return T10_OK;
+  k_tg_signal<<<1, 32, 0, (cudaStream_t)stream>>>(sig);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
+extern "C" int t10_wait_flags(int n, const void* const* h_flags, const uint64_t* h_need, int64_t timeout_ms,
+                              int32_t* d_err, t10_stream_t stream) {
+  T10_REQUIRE(n >= 0 && n <= 8 && (n == 0 || (h_flags && h_need)), T10_ERR_INVALID, "wait_flags: 0..8 flags");
+  if (n == 0) return T10_OK;
+  TgWait w;
+  memset(&w, 0, sizeof(w));
+  w.n = n;
+  for (int i = 0; i < n; ++i) {
+    w.flag[i] = (const unsigned long long*)h_flags[i];
+    w.need[i] = h_need[i];
+  }
+  w.timeout_ns = timeout_ms > 0 ? (unsigned long long)timeout_ms * 1000000ull : 0ull;
+  w.err = d_err;
+  k_tg_wait<<<1, 32, 0, (cudaStream_t)stream>>>(w);
+  T10_LAUNCH_CHECK();
+  return T10_OK;
+}
+
 extern "C" int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const t10_gemm_problem* d_prob,
                              int64_t npieces, const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
                              const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch, int pdl,
+                             int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr,
                              t10_stream_t stream) {
-  if (npieces == 0 || nprob == 0) return T10_OK;
+  TgSignal sig;
+  {
+    int rc = tg_fill_signal(&sig, nsig, h_sig_flags, sig_value, d_done_ctr);
+    if (rc != T10_OK) return rc;
+  }
+  if (npieces == 0 || nprob == 0) {      // a rank without work still has to signal
+    if (nsig > 0) {
+      k_tg_signal<<<1, 32, 0, (cudaStream_t)stream>>>(sig);
+      T10_LAUNCH_CHECK();
+    }
+    return T10_OK;
+  }
   T10_REQUIRE(npieces > 0 && nprob > 0 && nslots >= 1, T10_ERR_INVALID, "ggemm_tma: bad counts");
   T10_REQUIRE(d_maps && d_pieces && d_tiles && d_slot_start && d_ws && d_flags, T10_ERR_INVALID, "ggemm_tma: missing table");
   T10_REQUIRE(((uintptr_t)d_maps & 63) == 0, T10_ERR_INVALID, "ggemm_tma: tensor maps must be 64-byte aligned");
@@ -365,15 +493,20 @@ extern "C" int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)nslots);
   cfg.blockDim = dim3(TG_THREADS);
-  cfg.dynamicSmemBytes = TG_SMEM_BYTES;
+  cfg.dynamicSmemBytes = tg_variant() == 3 ? tg_smem_bytes(3) : tg_smem_bytes(4);
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  T10_CUDA(cudaLaunchKernelEx(&cfg, k_ggemm_f64_tma, (const CUtensorMap*)d_maps, (double*)d_C, d_prob,
-                              (const int4*)d_tiles, (const int4*)d_pieces, d_slot_start, (double*)d_ws, (int*)d_flags,
-                              (int)epoch, pdl, ggemm_trace_ptr()));
+  if (tg_variant() == 3)
+    T10_CUDA(cudaLaunchKernelEx(&cfg, k_ggemm_f64_tma<3, 3>, (const CUtensorMap*)d_maps, (double*)d_C, d_prob,
+                                (const int4*)d_tiles, (const int4*)d_pieces, d_slot_start, (double*)d_ws, (int*)d_flags,
+                                (int)epoch, pdl, ggemm_trace_ptr(), sig));
+  else
+    T10_CUDA(cudaLaunchKernelEx(&cfg, k_ggemm_f64_tma<4, 2>, (const CUtensorMap*)d_maps, (double*)d_C, d_prob,
+                                (const int4*)d_tiles, (const int4*)d_pieces, d_slot_start, (double*)d_ws, (int*)d_flags,
+                                (int)epoch, pdl, ggemm_trace_ptr(), sig));
   return T10_OK;
 }

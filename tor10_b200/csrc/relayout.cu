@@ -20,6 +20,7 @@
 // in registers) and walks the rows of its tile with the loads of several rows in flight.
 // Source sectors (32 B) touched by neighbouring rows of a tile are served from L1.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "t10_common.cuh"
@@ -531,7 +532,12 @@ extern "C" int t10_relayout_segments(int dtype, int nsrc, const void* const* h_s
   memset(&ss, 0, sizeof(ss));
   for (int i = 0; i < nsrc; ++i) ss.base[i] = h_src[i];
   const int64_t warps = nseg;
-  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(warps, RS_THREADS / 32), (int64_t)sm_count() * 8));
+  static int rs_ctas = 0;        // CTAs per SM (TOR10_RELAYOUT_SEG_CTAS, default 6 = the register limit)
+  if (rs_ctas == 0) {
+    const char* e = getenv("TOR10_RELAYOUT_SEG_CTAS");
+    rs_ctas = e ? std::max(1, std::min(8, atoi(e))) : 6;
+  }
+  unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(warps, RS_THREADS / 32), (int64_t)sm_count() * rs_ctas));
   if (dtype == T10_F64)
     k_relayout_segments<double><<<grid, RS_THREADS, 0, st>>>(ss, (double*)d_dst, (const int4*)d_seg, (int)nseg);
   else if (dtype == T10_F32)

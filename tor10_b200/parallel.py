@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-_STATE = {"group": None, "enabled": False, "transport": "auto"}
+_STATE = {"group": None, "enabled": False, "transport": "auto", "shard": None}
 
 
 def enable(group=None, transport="auto"):
@@ -24,14 +24,22 @@ def enable(group=None, transport="auto"):
                   "p2p"   = symmetric-memory staging + device barrier + one pull kernel over NVLink peer memory,
                   "nccl"  = all_gather_into_tensor through a staging buffer,
                   "none"  = results stay sharded: every rank holds only its own sectors (others are zero),
+                  "resident" = results stay sector-RESIDENT: every rank keeps the sectors it computed, the tensor
+                           carries an owner table, later contractions read it in place / fetch foreign sectors
+                           from their owners over NVLink, and anything that needs the whole tensor gathers it
+                           on demand (see the second half of this module),
+                  "pull"  = resident, then every rank pulls the other ranks' sectors at once (gathered result,
+                           no staging copy),
                   "auto"  = fused on NCCL process groups when symmetric memory is available, else nccl."""
     if not dist.is_initialized():
         raise RuntimeError("tor10_b200.parallel.enable(): torch.distributed is not initialised")
-    if transport not in ("auto", "fused", "p2p", "nccl", "none"):
-        raise ValueError("transport must be auto | fused | p2p | nccl | none")
+    if transport not in ("auto", "fused", "p2p", "nccl", "none", "resident", "pull"):
+        raise ValueError("transport must be auto | fused | p2p | nccl | none | resident | pull")
     _STATE["group"] = group
     _STATE["enabled"] = True
     _STATE["transport"] = transport
+    world = dist.get_world_size(group)
+    _STATE["shard"] = None if world == 1 else (dist.get_rank(group), world)
 
 
 def disable():
@@ -42,11 +50,7 @@ def current_shard():
     """(rank, world) when sector sharding is on, else None."""
     if not _STATE["enabled"]:
         return None
-    g = _STATE["group"]
-    world = dist.get_world_size(g)
-    if world == 1:
-        return None
-    return (dist.get_rank(g), world)
+    return _STATE["shard"]
 
 
 def partition_contiguous(cost, parts):
@@ -111,6 +115,7 @@ def arena_ranges(layout, bounds):
 
 _STAGE = {}
 _SYMM = {}
+import os as _os
 
 
 class _SymmStaging:
@@ -168,7 +173,9 @@ def transport_for(group=None):
         return "nccl"          # (gloo tests: broadcast path inside gather_ranges)
     try:
         import torch.distributed._symmetric_memory  # noqa: F401
-        return "fused"         # GEMM with the all-gather in its epilogue; plans that cannot fuse pull (p2p)
+        # results stay sector-resident (gathered on demand); TOR10_TRANSPORT_AUTO=fused restores the round-1 default
+        # (GEMM with the all-gather in its epilogue; plans that cannot fuse pull)
+        return _os.environ.get("TOR10_TRANSPORT_AUTO", "resident")
     except Exception:
         return "nccl"
 
@@ -257,3 +264,253 @@ def gather_ranges(arena, ranges, rank, group=None):
         if r != rank and phi > plo:
             arena[plo:phi].copy_(stage[r * max_len:r * max_len + (phi - plo)])
     return arena
+
+
+# ======================================================================================================
+# Sector-RESIDENT tensors ("preferred: keep tensors sector-sharded across consecutive
+# contractions; ownership propagates").
+#
+# transport "resident": Contract() returns a tensor of which every rank holds only the sectors it computed.
+# Nothing is gathered.  The tensor carries an owner table; a later Contract adopts it (output sector q lives
+# where A's row sector q lives), reads what it owns in place and fetches the few foreign sectors it needs
+# straight out of the owner's arena through NVLink peer mappings (inside the relayout copy, or by a pull
+# kernel) -- no collective on the data path.  Anything that needs the whole tensor (`.Storage`, GetBlock,
+# arithmetic, pickling, printing) gathers it on demand, once.
+#
+# Synchronisation is a single monotone PROGRESS WORD per rank, in symmetric memory (peers can read it):
+#   * every resident operation has a sequence number (all ranks issue the same operations in the same order:
+#     SPMD, the contract of torch.distributed itself); the kernel that completes operation s on rank r stores s
+#     into rank r's OWN word (a local st.release.sys, t10_ggemm_tma / t10_signal_flags) -- measured: storing it
+#     into the peers' copies instead cost 12.5 us per Contract at 2 GPUs, the latency of one NVLink store;
+#   * read-after-write: before a kernel reads sectors rank p produced in operation s it acquires word p >= s,
+#     polling it REMOTELY through the NVLink mapping -- only a reader that needs foreign data pays for the link;
+#   * write-after-read: result arenas come from a small ring per plan (symmetric memory, so peers can read
+#     them); before a slot is overwritten the ranks acquire every peer's word >= the last operation that read it.
+# Waits are one-warp kernels (t10_wait_flags); they are skipped when the host already knows the value was
+# acquired on the stream.  A bounded wait that expires traps (never continue on
+# a timeout).
+# ======================================================================================================
+import os as _os
+import weakref as _weakref
+
+_RES = {"world": None}
+WAIT_TIMEOUT_MS = int(_os.environ.get("TOR10_WAIT_TIMEOUT_MS", "20000"))
+POOL_DEPTH = int(_os.environ.get("TOR10_RESIDENT_POOL", "4"))
+
+
+class Residency:
+    """Where the sectors of a resident tensor live.  owner[s] = rank that computed sector s (-1: nobody, the
+    sector is zero everywhere); valid[s] = this rank's arena holds sector s; seq = the operation that produced
+    it (read-after-write bound on the owners' progress words)."""
+    __slots__ = ("world", "rank", "owner", "valid", "seq", "slot", "__weakref__")
+
+    def __init__(self, world, rank, owner, seq, slot, own_valid=None):
+        self.world, self.rank = world, rank
+        self.owner = owner                     # (shared with the plan: never modified)
+        self.valid = ((np.asarray(owner) == rank) | (np.asarray(owner) < 0)) if own_valid is None else own_valid.copy()
+        self.seq, self.slot = seq, slot
+
+    def key(self):
+        return (self.world, self.owner.tobytes())
+
+
+class _Slot:
+    __slots__ = ("pool", "index", "holder", "last_read")
+
+    def __init__(self, pool, index):
+        self.pool, self.index, self.holder, self.last_read = pool, index, None, 0
+
+    def tensor(self):
+        return self.pool.bufs[self.index]
+
+    def peer_ptr(self, r):
+        return self.pool.peer_ptrs[self.index][r]
+
+
+class ArenaPool:
+    """Ring of POOL_DEPTH result arenas of one plan in ONE symmetric-memory allocation (peers read resident
+    sectors out of them).  Regions no rank ever writes (unmatched sectors, padding) stay zero."""
+
+    def __init__(self, rw, n, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rw, self.n, self.dtype = rw, int(n), dtype
+        self.stride = (self.n + 63) // 64 * 64
+        esz = torch.empty(0, dtype=dtype).element_size()
+        whole = symm_mem.empty(POOL_DEPTH * self.stride, dtype=dtype, device=device)
+        whole.zero_()
+        torch.cuda.synchronize(device)
+        hdl = symm_mem.rendezvous(whole, group=rw.group_or_world())
+        self.whole, self.hdl = whole, hdl
+        self.bufs = [whole[k * self.stride:k * self.stride + self.n] for k in range(POOL_DEPTH)]
+        base = [int(hdl.get_buffer(r, (POOL_DEPTH * self.stride,), dtype).data_ptr()) for r in range(rw.world)]
+        self.peer_ptrs = [[base[r] + k * self.stride * esz for r in range(rw.world)] for k in range(POOL_DEPTH)]
+        self.slots = [_Slot(self, k) for k in range(POOL_DEPTH)]
+        self.turn = 0
+        dist.barrier(group=rw.group)
+
+    def acquire(self):
+        """Next slot of the ring.  A tensor still living in it is gathered out first (every rank does so at the
+        same program point).  Returns (slot, write-after-read bound)."""
+        slot = self.slots[self.turn]
+        self.turn = (self.turn + 1) % POOL_DEPTH
+        old = slot.holder() if slot.holder is not None else None
+        if old is not None and getattr(old, "_res", None) is not None and old._res.slot is slot:
+            old._materialize()
+        slot.holder = None
+        return slot, slot.last_read
+
+
+class ResidentWorld:
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.progress = symm_mem.empty(8, dtype=torch.int64, device=device)      # word 0 = this rank's progress
+        self.progress.zero_()
+        torch.cuda.synchronize(device)
+        hdl = symm_mem.rendezvous(self.progress, group=self.group_or_world())
+        self.hdl = hdl
+        import ctypes as C
+        # the producer stores into its OWN word only; readers poll the word of the rank they depend on (a peer's
+        # through its NVLink mapping), so a rank that nobody waits for generates no link traffic at all
+        self.word_ptrs = (C.c_void_p * self.world)(*[int(hdl.get_buffer(r, (8,), torch.int64).data_ptr())
+                                                     for r in range(self.world)])
+        self.sig_ptrs = (C.c_void_p * 1)(int(self.progress.data_ptr()))
+        self.done_ctr = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.seq = 0
+        self.acquired = {}          # stream -> per-rank value known to have been acquired on it
+        self.pools = {}
+        dist.barrier(group=group)
+
+    def group_or_world(self):
+        return self.group if self.group is not None else dist.group.WORLD
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+    def wait(self, need):
+        """Acquire progress[r] >= need[r] on the current stream (a one-warp kernel; skipped when known)."""
+        if not any(need):
+            return False
+        import ctypes as C
+        from . import _lib
+        st = _lib.stream_ptr()
+        have = self.acquired.setdefault(st, [0] * self.world)
+        have[self.rank] = max(have[self.rank], self.seq)      # this rank's own operations are stream-ordered
+        need = [int(x) for x in need]
+        if all(n <= h for n, h in zip(need, have)):
+            return False
+        arr = (C.c_uint64 * self.world)(*[max(n, 0) for n in need])
+        _lib.check(_lib.load().t10_wait_flags(self.world, self.word_ptrs, arr, WAIT_TIMEOUT_MS,
+                                              self.err.data_ptr(), st))
+        for r in range(self.world):
+            have[r] = max(have[r], need[r])
+        return True
+
+    def signal(self, value):
+        """Publish `value` as this rank's progress from a one-warp kernel (after read-only operations)."""
+        from . import _lib
+        _lib.check(_lib.load().t10_signal_flags(1, self.sig_ptrs, int(value), _lib.stream_ptr()))
+
+    def pool(self, key, n, dtype, device):
+        p = self.pools.get(key)
+        if p is None:
+            p = ArenaPool(self, n, dtype, device)
+            self.pools[key] = p
+        return p
+
+
+def resident_world(device=None):
+    rw = _RES["world"]
+    if rw is None:
+        if dist.get_backend(_STATE["group"]) != "nccl":
+            raise RuntimeError("tor10_b200.parallel: resident tensors need NVLink peer memory (NCCL process group)")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        rw = ResidentWorld(_STATE["group"], device)
+        _RES["world"] = rw
+    return rw
+
+
+def reset_resident():
+    _RES["world"] = None
+
+
+def inherit_owner(a_owner, matched, nsec_out, cost, world):
+    """Ownership of the output sectors of a contraction whose first operand is resident and read in place: output
+    sector q lives where A's row sector q lives; sectors A's table does not place (owner -1: A's
+    sector is zero) and unmatched ones go to nobody.  Pure function (tested on the CPU)."""
+    owner = np.full(nsec_out, -1, dtype=np.int64)
+    for ob, ab, _ in matched:
+        owner[ob] = a_owner[ab]
+    return owner
+
+
+def fetch_plan(layout, res, needed):
+    """Which of the `needed` sectors this rank must pull, grouped by owner: {owner: [(lo, hi), ...]} arena ranges.
+    Pure function (tested on the CPU)."""
+    out = {}
+    for s in needed:
+        if res.valid[s]:
+            continue
+        o = int(res.owner[s])
+        lo = int(layout.arena_off[s])
+        hi = lo + int(layout.rows[s]) * int(layout.ld[s])
+        hi = (hi + 3) // 4 * 4          # whole 16-byte vectors in fp32 too (sector bases are 16-element aligned)
+        out.setdefault(o, []).append((lo, hi))
+    return out
+
+
+def pull_sectors(t, needed):
+    """Make the `needed` sectors of resident tensor t valid in this rank's arena: one pull kernel over the owners'
+    NVLink peer mappings (after acquiring their progress).  No-op for sectors already here."""
+    import ctypes as C
+    from . import _lib
+    res = t._res
+    plan = fetch_plan(t._layout, res, needed)
+    if not plan:
+        return
+    rw = resident_world()
+    if res.slot is None:
+        raise RuntimeError("tor10_b200.parallel: this resident tensor no longer lives in peer-readable memory")
+    need = [0] * rw.world
+    for o in plan:
+        need[o] = res.seq
+    rw.wait(need)
+    segs = [(res.slot.peer_ptr(o), lo, hi) for o, rs in sorted(plan.items()) for lo, hi in rs]
+    arena = t._arena
+    for i in range(0, len(segs), 16):
+        part = segs[i:i + 16]
+        n = len(part)
+        _lib.check(_lib.load().t10_gather_peers(
+            _lib.dtype_code(arena.dtype), arena.data_ptr(), n, (C.c_void_p * n)(*[p for p, _, _ in part]),
+            (C.c_int64 * n)(*[a for _, a, _ in part]), (C.c_int64 * n)(*[b for _, _, b in part]), _lib.stream_ptr()))
+    for s in needed:
+        res.valid[s] = True
+    # the peers read THIS rank's slot the same way: they are done once they have published their next operation
+    res.slot.last_read = max(res.slot.last_read, rw.seq + 1)
+
+
+def materialize(t):
+    """Gather a resident tensor on demand: pull every foreign sector, publish the read (so the owners may reuse
+    their slots), move the tensor into private memory.  Every rank that holds the tensor must call this at the
+    same program point if it calls it at all (SPMD); ranks that never look at the whole tensor never pay for it."""
+    res = t._res
+    if res is None:
+        return
+    rw = resident_world()
+    if res.slot is not None:
+        pull_sectors(t, [s for s in range(len(res.owner)) if not res.valid[s]])
+        seq = rw.next_seq()
+        res.slot.last_read = max(res.slot.last_read, seq)
+        rw.signal(seq)
+        t._arena = t._arena.clone()
+        if res.slot.holder is not None and res.slot.holder() is t:
+            res.slot.holder = None
+    elif not res.valid.all():
+        raise RuntimeError("tor10_b200.parallel: resident tensor is incomplete and its peers' memory is gone")
+    t._res = None
+    t._blocks = None
