@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 RELAYOUT_TRAFFIC = {"index": 37.73e6, "runs": None}   # filled from the ncu captures under profiles/
-METRIC = "U1 block-sparse Contract GFLOP/s (fp64) at chi=4096"
+METRIC = "U1 block-sparse Contract GFLOP/s (fp64) at chi=4096"      # (+ "; iTEBD steps/sec": the `itebd` object)
 UNIT = "GFLOP/s"
 
 
@@ -145,6 +145,49 @@ def oracle_parity(chi, c):
             ":3692-3743, pinned to the reference's fixtures) on the same seeded operands, full size"}
 
 
+def itebd_leg(budget_s=25.0):
+    """Second half of the BASELINE metric: iTEBD steps per second (config 1: `iTEBD.py 1.0 0.5 32 1e-8`, untagged
+    tensors, fp64, the whole run to convergence from a seeded random state).  `steps_per_s` is the B200-native path
+    (the step captured into one CUDA graph, examples/itebd.py run_graphed); `eager_steps_per_s` is the unmodified
+    drop-in script path (one Python call per library call, `.item()` every step); `cpu_port_steps_per_s` is the
+    numpy restatement of the reference loop on the host cores (checker / baseline only)."""
+    import importlib.util
+    import torch
+    from oracle import itebd_numpy as it
+    spec = importlib.util.spec_from_file_location("itebd_example", os.path.join(ROOT, "examples", "itebd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    chi, J, Hx, cvg = 32, 1.0, 0.5, 1e-8
+    rng = np.random.Generator(np.random.PCG64(1234))
+    init = {"A": rng.random((chi, 2, chi)), "B": rng.random((chi, 2, chi)), "la": rng.random(chi), "lb": rng.random(chi)}
+    cap = 20000
+    ex.run(J, Hx, chi, 0.0, max_steps=20, init=init)                      # plans / caches warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rg = ex.run_graphed(J, Hx, chi, cvg, max_steps=cap, init=init)
+    torch.cuda.synchronize()
+    tg = time.perf_counter() - t0
+    n_eager = min(rg["steps"], max(200, int(budget_s * 0.4 / 0.002)))    # a bounded prefix of the same run
+    t0 = time.perf_counter()
+    re_ = ex.run(J, Hx, chi, 0.0, max_steps=n_eager, init=init)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rc = it.run(J, Hx, chi, cvg, max_steps=cap, init=init)
+    tc = time.perf_counter() - t0
+    ne_ = min(len(re_["energies"]), len(rc["energies"]))
+    ng = min(len(rg["energies"]), len(rc["energies"]))
+    return {"config": "transverse-field Ising chain J=1.0 Hx=0.5 chi=32 cvg=1e-8, untagged UniTensors, fp64, PCG64(1234) start",
+            "steps": rg["steps"], "E": rg["E"], "steps_per_s": rg["steps"] / tg, "ms_per_step": tg / rg["steps"] * 1e3,
+            "path": "step captured into one CUDA graph (tor10_b200.graph.StaticLoop); energy read back every step",
+            "eager_steps_per_s": n_eager / te, "eager_ms_per_step": te / n_eager * 1e3, "eager_steps_timed": n_eager,
+            "cpu_port_steps_per_s": rc["steps"] / tc, "cpu_port_steps": rc["steps"], "E_cpu_port": rc["E"],
+            "cores": os.cpu_count() or 1,
+            "max_abs_dE_vs_cpu_port": float(np.abs(np.array(rg["energies"][:ng]) - np.array(rc["energies"][:ng])).max()),
+            "max_abs_dE_eager_vs_cpu_port": float(np.abs(np.array(re_["energies"][:ne_]) - np.array(rc["energies"][:ne_])).max()),
+            "svd": "one-CTA Jacobi kernel (t10_svd_small, warm-started); cuSOLVER gesvdj on this matrix: 1.8 ms"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chi", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-itebd", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="warmup + steps only (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -561,6 +605,11 @@ def main():
         "parity": parity,
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }
+    if world == 1 and not args.no_itebd:
+        try:
+            line["itebd"] = itebd_leg()
+        except Exception as exc:
+            line["itebd"] = {"error": repr(exc)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         cf, ctimes = cpu_port_run(args.chi, budget_s=12.0, max_reps=20)
         ct = float(np.mean(ctimes[1:] or ctimes))

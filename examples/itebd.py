@@ -90,6 +90,41 @@ def run(J, Hx, chi, cvg, max_steps=100000, init=None, verbose=False, check_every
             "state": (A, B, la, lb)}
 
 
+def run_graphed(J, Hx, chi, cvg, max_steps=100000, init=None, check_every=1, verbose=False):
+    """The same algorithm with the step captured into ONE CUDA graph (tor10_b200.graph.StaticLoop): ~45 launches per
+    step become one graph launch.  `check_every` steps apart the energy is read back and the convergence test runs."""
+    from tor10_b200.graph import StaticLoop
+    dev = torch.device("cpu")
+    H, eH = two_site_gate(J, Hx, device=dev)
+    A, B, la, lb = initial_state(chi, dev, init)
+    warm = 3
+    energies_warm = []
+
+    def counted(A, B, la, lb, H, eH, chi):
+        out = step(A, B, la, lb, H, eH, chi)
+        energies_warm.append(out[4])
+        return out
+
+    loop = StaticLoop(counted, state=(A, B, la, lb), consts=(H, eH, chi), warmup=warm)
+    energies = [float(e.item()) for e in energies_warm[:warm]]       # the eager warm-up steps are steps of the run
+    Elast = energies[-2] if len(energies) > 1 else 0.0
+    i = warm - 1
+    if abs(energies[-1] - Elast) >= cvg:
+        Elast = energies[-1]
+        for i in range(warm, max_steps):
+            (E,) = loop()
+            if (i + 1) % check_every:
+                continue
+            E = float(E.item())
+            energies.append(E)
+            if verbose:
+                print("Energy = {:.6f}".format(E))
+            if abs(E - Elast) < cvg:
+                break
+            Elast = E
+    return {"steps": i + 1, "E": energies[-1], "energies": energies, "state": loop.state}
+
+
 if __name__ == "__main__":
     if len(sys.argv) < 5:
         print(".py <J> <Hx> <chi> <converge> [max_steps]")

@@ -308,6 +308,28 @@ int t10_ggemm_allgather(int tile_cfg, const void* d_A, const void* d_B, int npee
 int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t n, const void* d_flags, int nflags,
                   uint64_t step, int32_t* d_err, t10_stream_t stream);
 
+/* ------------------------------------------------------------------ small SVD ---- */
+
+/* Batched SVD of small matrices, one CTA per matrix: one-sided Jacobi in shared memory (replaces cuSOLVER behind
+ * `torch.svd(a.Storage, some=True)` of Svd / Svd_truncate, linalg.py:544-678, for matrices that fit one SM -- the
+ * 64 x 64 matrix of every iTEBD.py step costs cuSOLVER 1.8 ms on a B200).  h_prob: nine int64 per matrix
+ * {m, n, a_off, row_stride, col_stride, u_off, s_off, v_off, w_off} with m >= n, n <= 64 and (m + n') * n' * sizeof <= 200 KB
+ * (n' = n rounded up to even; t10_svd_small_limits); element (r, c) of matrix i is d_A[a_off + r * row_stride +
+ * c * col_stride] (a wide matrix is passed transposed through its strides).  Writes U [m, n] row-major at
+ * d_U + u_off, the singular values, descending, at d_S + s_off and Vh [n, n] row-major at d_Vh + v_off, so that
+ * A = U diag(S) Vh.  A zero singular value gets a zero U column.  d_info[i] (may be NULL): bit 0 = matrix i was still
+ * rotating after 40 sweeps, bits 1.. = sweeps run.  d_W (may be NULL) + w_off >= 0: warm-start state of the matrix,
+ * T10_SVD_WARM_ELEMS(n) elements, zero-initialised by the caller and then left to the kernel -- a ring of two slots
+ * used in turn, each keeping the right singular vectors of the call before last on this state, from which the
+ * rotations start (any orthogonal start converges; a slowly changing sequence of matrices -- or two interleaved
+ * ones, as in iTEBD's alternating bonds -- then needs 2-3 sweeps instead of 10-20); every slot restarts from the
+ * identity every 64 uses.  Warm start needs m * n more elements of shared memory.
+ * No allocation, no copy, no synchronisation: capturable into a CUDA graph.                                  */
+#define T10_SVD_WARM_ELEMS(n) (2 * ((n) * (n) + 1) + 1)
+int t10_svd_small_limits(int* max_n, int* max_elems);
+int t10_svd_small(int dtype, int64_t nprob, const int64_t* h_prob, const void* d_A, void* d_U, void* d_S,
+                  void* d_Vh, void* d_W, int32_t* d_info, t10_stream_t stream);
+
 /* Profiling aid: while d_trace != NULL the fp64 tensor-core kernels record, per tile t of the tile table,
  * d_trace[4t..4t+3] = {SM id, CTA, globaltimer at start, globaltimer at end} (uint64).  NULL turns it off. */
 int t10_ggemm_set_trace(void* d_trace);

@@ -159,6 +159,19 @@ class Emu:
             o = arr(dst + d * isz, ln, fd)
             o[:] = 0 if s_ < 0 else arr(bases[w] + s_ * isz, ln, fd)
         return 0
+    def t10_svd_small_limits(self, mn, me):
+        mn._obj.value = 64; me._obj.value = 25600
+        return 0
+    def t10_svd_small(self, dt, nprob, prob, A, U, S, Vh, W, info, st):
+        fd = np.float64 if dt == 0 else np.float32
+        isz = np.dtype(fd).itemsize
+        pr = arr(prob, 9 * nprob, np.int64).reshape(nprob, 9)
+        for m, n, ao, rs, cs, uo, so, vo, wo in pr.tolist():
+            span = (m - 1) * rs + (n - 1) * cs + 1
+            a = np.lib.stride_tricks.as_strided(arr(A + ao * isz, span, fd), (m, n), (rs * isz, cs * isz))
+            u, s_, vh = np.linalg.svd(a, full_matrices=False)
+            arr(U + uo * isz, m * n, fd)[:] = u.reshape(-1); arr(S + so * isz, n, fd)[:] = s_; arr(Vh + vo * isz, n * n, fd)[:] = vh.reshape(-1)
+        return 0
     def t10_ggemm_tma_slots(self, out):
         out._obj.value = 296
         return 0
@@ -187,6 +200,7 @@ class Emu:
 
 emu = Emu()
 _lib.load = lambda: emu
+_lib._EMU = True
 _lib.require_cuda = lambda d: torch.device(d)
 _lib.stream_ptr = lambda: 0
 class _NoDev:

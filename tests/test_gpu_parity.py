@@ -579,6 +579,28 @@ def test_itebd_trajectory_matches_reference(T):
     assert np.abs(got - z["energies"]).max() <= 1e-9
 
 
+def test_itebd_graphed_matches_eager_and_reference(T):
+    """The same loop with the step captured into one CUDA graph (tor10_b200.graph.StaticLoop, examples/itebd.py
+    run_graphed): energies equal the eager run's and the unmodified reference's, step by step."""
+    if DEV != "cuda":
+        pytest.skip("CUDA graphs need the device")
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("itebd_example", os.path.join(root, "examples", "itebd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    z = np.load(os.path.join(root, "tests", "golden", "itebd.npz"))
+    sp = json.loads(str(z["specs"]))
+    init = {k: z[k] for k in ("A", "B", "la", "lb")}
+    eager = np.array(ex.run(sp["J"], sp["Hx"], sp["chi"], 0.0, max_steps=sp["nsteps"], init=init)["energies"])
+    out = ex.run_graphed(sp["J"], sp["Hx"], sp["chi"], 0.0, max_steps=sp["nsteps"], init=init)
+    got = np.array(out["energies"])
+    assert out["steps"] == sp["nsteps"] and got.shape == z["energies"].shape
+    assert np.abs(got - eager).max() <= 1e-12
+    assert np.abs(got - z["energies"]).max() <= 1e-9
+
+
 def test_permute_without_common_sector_keeps_an_empty_table(T):
     """The reference's Permute only recomputes `_block_qnums` (UniTensor.py:2310-2313): when the new row and column
     spaces share no charge the table is EMPTY and nothing raises until the tensor is relaid out (found by

@@ -221,6 +221,24 @@ class UniTensor:
 
     _res = None      # parallel.Residency of a sector-resident Contract result (multi-GPU), else None
 
+    # Dense storage.  `_diag_hint` remembers that a DENSE rank-2 storage is known to be diag(hint): the reference
+    # densifies a diagonal tensor as soon as it is multiplied by a rank-0 tensor (UniTensor.py __mul__: torch.diag),
+    # which is what iTEBD.py does to the singular values every step (`la *= la.Norm()**-1`), and then pays chi^3
+    # GEMMs and an LU inverse for what are scalings.  The visible tensor stays dense as in the reference; Contract
+    # and Inverse use the hint.  Any reassignment of the storage, and any access that hands the storage out
+    # (`.Storage`, __setitem__), drops it.
+    @property
+    def _dense(self):
+        return self.__dict__.get("_dn")
+
+    @_dense.setter
+    def _dense(self, v):
+        d = self.__dict__
+        d["_dn"] = v
+        d["_diag_hint"] = None
+
+    _diag_hint = None
+
     def _materialize(self):
         """A sector-resident result (parallel transport "resident") is gathered the first time something needs the
         whole tensor; until then every rank holds only the sectors it computed."""
@@ -257,6 +275,7 @@ class UniTensor:
             if self._blocks is None:
                 self._blocks = _BlockList(self._layout.views(self._arena))
             return self._blocks
+        self.__dict__["_diag_hint"] = None        # the caller may modify the tensor it gets
         return self._dense
 
     @Storage.setter
@@ -605,6 +624,7 @@ class UniTensor:
         if self.is_symm:
             raise Exception("UniTensor.__setitem__",
                             "[ERROR] cannot use [] to setitem from a block-form tensor. Use get block first.")
+        self.__dict__["_diag_hint"] = None
         self._dense[key] = value
 
     def item(self):
@@ -644,7 +664,10 @@ class UniTensor:
             if self.is_diag and other.is_diag:
                 return self._like(f(self._dense, other._dense), is_diag=True)
             if self.is_diag:
-                return self._like(f(torch.diag(self._dense), other._dense), is_diag=False)
+                t = self._like(f(torch.diag(self._dense), other._dense), is_diag=False)
+                if other._dense.dim() == 0 and op in (torch.mul, torch.div) and not reverse:
+                    t.__dict__["_diag_hint"] = f(self._dense, other._dense)      # still diag(d * c)
+                return t
             if other.is_diag:
                 return self._like(f(self._dense, torch.diag(other._dense)), is_diag=False)
             return self._like(f(self._dense, other._dense), is_diag=False)
@@ -683,7 +706,9 @@ class UniTensor:
         if self.is_symm:
             self._arena, self._blocks = res._arena, None
         else:
+            hint = res._diag_hint
             self._dense, self.is_diag = res._dense, res.is_diag
+            self.__dict__["_diag_hint"] = hint
         return self
 
     def __iadd__(self, other):
@@ -1096,8 +1121,10 @@ class UniTensor:
                 t._blocks = None
             elif k == "_layout":
                 t._layout = v
-            elif k == "_dense":
-                t._dense = None if v is None else v.clone()
+            elif k == "_dn":
+                t.__dict__["_dn"] = None if v is None else v.clone()
+            elif k == "_diag_hint":
+                t.__dict__["_diag_hint"] = None if v is None else v.clone()
             elif k == "bonds":
                 t.bonds = np.array([copy.copy(b) for b in v], dtype=object)
             else:
@@ -1276,14 +1303,16 @@ def Contract(a, b):
         with _lib.on_device(a._dense.device):
             # a diagonal operand sharing ONE bond scales the other tensor along that bond; the reference
             # densifies it with torch.diag and runs a chi^3 GEMM (UniTensor.py:3756-3765)
-            if b.is_diag and not a.is_diag and len(same) == 1:
+            a_dg = a._dense if a.is_diag else a._diag_hint         # 1-D diagonal of a (stored, or known: see _dense)
+            b_dg = b._dense if b.is_diag else b._diag_hint
+            if b_dg is not None and a_dg is None and len(same) == 1:
                 ax = a_ind[0]
-                t = _diag_scale(a._dense, b._dense, ax)
+                t = _diag_scale(a._dense, b_dg, ax)
                 order = [i for i in range(t.dim()) if i != ax] + [ax]
                 tmp = t.permute(*order) if order != list(range(t.dim())) else t
-            elif a.is_diag and not b.is_diag and len(same) == 1:
+            elif a_dg is not None and b_dg is None and len(same) == 1:
                 ax = b_ind[0]
-                t = _diag_scale(b._dense, a._dense, ax)
+                t = _diag_scale(b._dense, a_dg, ax)
                 order = [ax] + [i for i in range(t.dim()) if i != ax]
                 tmp = t.permute(*order) if order != list(range(t.dim())) else t
             else:

@@ -75,6 +75,8 @@ SIGNATURES = {
     "t10_ggemm_streamk_allgather": [_p, _p, _i, _i, _p, _p, C.c_uint64, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _p],
     "t10_reduce_slices": [_i, _p, _p, _l, _i, _p],
     "t10_relayout_segments": [_i, _i, _p, _p, _l, _p, _p],
+    "t10_svd_small_limits": [_p, _p],
+    "t10_svd_small": [_i, _l, _p, _p, _p, _p, _p, _p, _p, _p],
     "t10_ggemm_tma_slots": [_p],
     "t10_ggemm_tma_encode": [_l, _p, _p, _p, _p],
     "t10_ggemm_tma": [_p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _i, _i, _p, C.c_uint64, _p, _p],

@@ -797,6 +797,12 @@ class GemmGroup:
             if len(self._tma_maps) >= 16:
                 self._tma_maps.pop(next(iter(self._tma_maps)))
             self._tma_maps[key] = d_maps
+            if A.is_cuda and torch.cuda.is_current_stream_capturing():
+                # a captured upload re-reads its pinned source on every replay: keep it alive with the graph's maps
+                self._tma_pinned = getattr(self, "_tma_pinned", []) + [h]
+        if self.sk_parked and A.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("tor10_b200: this contraction cuts tiles across CTAs (stream-K flags carry a per-launch "
+                               "epoch) and cannot be captured into a CUDA graph; run it eagerly")
         self.sk_epoch = self.sk_epoch % 2000000000 + 1
         nsig, sig_ptrs, sig_val, done = (0, None, 0, None) if signal is None else \
             (len(signal[0]), signal[0], int(signal[1]), signal[2].data_ptr())

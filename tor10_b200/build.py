@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtor10_b200.so")
-SOURCES = ["blockmap.cu", "relayout.cu", "permute_tma.cu", "ggemm.cu", "ggemm_tma.cu", "ggemm_tf32.cu"]
+SOURCES = ["blockmap.cu", "relayout.cu", "permute_tma.cu", "ggemm.cu", "ggemm_tma.cu", "ggemm_tf32.cu", "svd_small.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "shared",

@@ -11,6 +11,7 @@ import os
 import numpy as np
 import torch
 
+from . import _lib
 from .Bond import Bond
 from .UniTensor import Contract, UniTensor, _dense_gemm
 
@@ -178,6 +179,55 @@ def Qdr(a):
     return tq, td, tr
 
 
+_SVD_SMALL = os.environ.get("TOR10_SVD_SMALL", "1") == "1"
+_SVD_LIMITS = []
+_SVD_WARM = os.environ.get("TOR10_SVD_WARM", "1") == "1"
+_SVD_STATE = {}
+
+
+def _svd_small(x):
+    """u, s, vh of a small 2-D CUDA matrix by the one-CTA Jacobi kernel (t10_svd_small: 64 x 64 in ~0.1 ms where
+    cuSOLVER needs 1.8 ms), or None when the matrix does not fit one SM (the caller then uses torch / cuSOLVER)."""
+    import ctypes as C
+    on_gpu = x.is_cuda or getattr(_lib, "_EMU", False)       # (_EMU: the C-ABI emulator of the CPU test suite)
+    if x.dim() != 2 or not on_gpu or x.dtype not in (torch.float64, torch.float32) or x.requires_grad:
+        return None
+    if not _SVD_LIMITS:
+        mn, me = C.c_int(0), C.c_int(0)
+        _lib.check(_lib.load().t10_svd_small_limits(C.byref(mn), C.byref(me)))
+        _SVD_LIMITS.extend([int(mn.value), int(me.value)])
+    m, n = int(x.shape[0]), int(x.shape[1])
+    wide = m < n
+    mm, nn = (n, m) if wide else (m, n)
+    ne = (nn + 1) // 2 * 2
+    if nn < 1 or nn > _SVD_LIMITS[0] or ((mm | 1) + (ne | 1)) * ne * x.element_size() > _SVD_LIMITS[1] * 8:
+        return None
+    rs, cs = int(x.stride(0)), int(x.stride(1))
+    if wide:
+        rs, cs = cs, rs
+    u = torch.empty((mm, nn), device=x.device, dtype=x.dtype)
+    s = torch.empty((nn,), device=x.device, dtype=x.dtype)
+    vh = torch.empty((nn, nn), device=x.device, dtype=x.dtype)
+    # warm-start state per (shape, dtype, device): consecutive SVDs of slowly changing matrices (iTEBD) start from
+    # the previous right singular vectors (t10_svd_small)
+    W = None
+    if _SVD_WARM and ((mm | 1) * (ne + nn) + (ne | 1) * ne) * x.element_size() + ne * ne <= _SVD_LIMITS[1] * 8:
+        key = (mm, nn, rs, cs, x.dtype, x.device.index)
+        W = _SVD_STATE.get(key)
+        if W is None:
+            if len(_SVD_STATE) >= 64:
+                _SVD_STATE.pop(next(iter(_SVD_STATE)))
+            W = _SVD_STATE[key] = torch.zeros(2 * (nn * nn + 1) + 1, device=x.device, dtype=x.dtype)   # T10_SVD_WARM_ELEMS
+    prob = (C.c_int64 * 9)(mm, nn, 0, rs, cs, 0, 0, 0, 0 if W is not None else -1)
+    with _lib.on_device(x.device):
+        _lib.check(_lib.load().t10_svd_small(_lib.dtype_code(x.dtype), 1, prob, x.data_ptr(), u.data_ptr(),
+                                             s.data_ptr(), vh.data_ptr(), W.data_ptr() if W is not None else None,
+                                             None, _lib.stream_ptr()))
+    if wide:          # A^T = u s vh  =>  A = vh^T s u^T
+        return vh.t(), s, u.t()
+    return u, s, vh
+
+
 def _svd(a, keepdim, who):
     _check_rank2(a, who)
     # torch.svd(some=True) of the reference == linalg.svd(full_matrices=False) with V = Vh^T.  Default cuSOLVER
@@ -185,8 +235,12 @@ def _svd(a, keepdim, who):
     # faster on B200 (tools/svd_drivers.py) but fails to converge on rank-deficient sector blocks and shifts
     # the iTEBD energy trajectory by 3e-9, so it is opt-in.
     x = a._dense
-    drv = os.environ.get("TOR10_SVD_DRIVER") if x.device.type == "cuda" else None
-    u, s, vh = torch.linalg.svd(x, full_matrices=False, driver=drv or None)
+    small = _svd_small(x) if _SVD_SMALL else None
+    if small is not None:
+        u, s, vh = small
+    else:
+        drv = os.environ.get("TOR10_SVD_DRIVER") if x.device.type == "cuda" else None
+        u, s, vh = torch.linalg.svd(x, full_matrices=False, driver=drv or None)
     tmp = _new_label_ref(a)
     if keepdim is not None:
         if keepdim < 0 or keepdim > len(s):
@@ -347,6 +401,13 @@ def Inverse(a):
         raise Exception("Inverse", "[ERROR] inverse should have UniTensor with rowrank=1")
     if a.is_diag:
         return _rank2(a._dense ** -1, bonds=a.bonds, labels=a.labels, is_diag=True)
+    if a._diag_hint is not None:
+        # a dense matrix known to be diag(d) (UniTensor._dense): its inverse is diag(1 / d) -- what the LU of
+        # torch.inverse computes for such a matrix, without the factorisation
+        r = a._diag_hint ** -1
+        out = _rank2(torch.diag(r), bonds=a.bonds, labels=a.labels)
+        out.__dict__["_diag_hint"] = r
+        return out
     return _rank2(torch.inverse(a._dense), bonds=a.bonds, labels=a.labels)
 
 
