@@ -19,7 +19,7 @@ A, B = bench.c3a_specs(int(os.environ.get("CHI", "4096")))
 a = psym(T, A, seed=1003, device=dev); b = psym(T, B, seed=1004, device=dev)
 single = [x.clone() for x in T.Contract(a, b).Storage]
 out = {}
-for tr in os.environ.get("TRANSPORTS", "fused,nccl").split(","):
+for tr in os.environ.get("TRANSPORTS", "resident,pull,fused,nccl").split(","):
     parallel.enable(transport=tr)
     _plan.clear_caches()
     first, repro, err = None, True, 0.0
@@ -30,7 +30,7 @@ for tr in os.environ.get("TRANSPORTS", "fused,nccl").split(","):
         repro = repro and all(torch.equal(x, y) for x, y in zip(first, c.Storage))
         err = max(err, max(float((x - y).abs().max() / x.abs().max()) for x, y in zip(single, c.Storage)))
     g = _plan.get_contract_plan(a, b).gemm
-    out[tr] = {"bit_reproducible": repro, "max_rel_err_vs_single": err, "tile_cfg": g.tile_cfg, "stream_k": bool(g.streamk)}
+    out[tr] = {"bit_reproducible": repro, "max_rel_err_vs_single": err, "tile_cfg": g.tile_cfg, "stream_k": bool(g.streamk), "tma": bool(getattr(g, "tma", False))}
     parallel.disable()
     _plan.clear_caches()
 res = [None] * dist.get_world_size()
