@@ -28,7 +28,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-RELAYOUT_TRAFFIC = {"index": 37.73e6, "runs": None}   # filled from the ncu captures under profiles/
+NCU_RAW = os.path.join(ROOT, "profiles", "r02_ncu_raw_final.csv")     # `ncu --set full` of this command, raw page
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the COMMITTED ncu capture of this
+    command (profiles/r02_ncu_raw_final.csv, C3a chi=4096, 1 GPU).  Fails loudly when the capture holds no launch of
+    the kernel the roofline names: a stale capture must not lend its traffic to another kernel."""
+    import csv
+    if not os.path.exists(NCU_RAW):
+        return None
+    rows = list(csv.reader(open(NCU_RAW)))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]] for r in rows[2:] if kernel in r[ki]]
+    assert vals, "profiles/r02_ncu_raw_final.csv holds no launch of %s: re-capture it" % kernel
+    return float(np.mean(vals))
 METRIC = "U1 block-sparse Contract GFLOP/s (fp64) at chi=4096"      # (+ "; iTEBD steps/sec": the `itebd` object)
 UNIT = "GFLOP/s"
 
@@ -578,9 +594,10 @@ def main():
                      # command at chi=4096 on 1 GPU (profiles/r01_ncu_summary.md): 49.97 MB + 4.21 MB (tile_cfg 40),
                      # 50.00 MB + 3.02 MB (tile_cfg 3)
                      # 50.74 MB + 11.09 MB (tile_cfg 46 as stream-K: the parked partial tiles add ~8 MB)
-                     "traffic": (None if getattr(plan.gemm, "tma", False) else
-                                 {46: 61.82e6, 40: 54.18e6, 3: 53.02e6}.get(plan.gemm.tile_cfg)
-                                 if (world == 1 and args.chi == 4096) else None),
+                     "traffic": (ncu_traffic("k_ggemm_f64_tma") if getattr(plan.gemm, "tma", False) else None)
+                     if (world == 1 and args.chi == 4096) else None,
+                     "traffic_source": "profiles/r02_ncu_raw_final.csv (ncu --set full of `bench.py --steps 2 --warmup 3 "
+                                       "--profile-only`, dram read + write per launch, L2 flushed before the launch)",
                      "algorithmic_bytes": 8.0 * plan.gemm.bytes, "ms": gemm_ms, "rank_share_of_flops": share,
                      "peak_source": "FP64 measured live in this run, best of 3 each: max(torch.matmul f64 8192^3 = %.1f TF, "
                                     "DMMA register probe = %.1f TF; DFMA probe = %.1f TF); MEASURED_PEAKS.json has "
@@ -599,9 +616,9 @@ def main():
                               "ms": rel_ms, "algorithmic_bytes": rel_bytes, "peak_source": hbm_src,
                               # dram read+write of one launch, ncu --set full at chi=4096 on 1 GPU
                               # (profiles/r01_ncu_summary.md); the destination partly stays in L2
-                              "traffic": (None if (plan.rel_a is not None and plan.rel_a.d_seg is not None) else
-                                          RELAYOUT_TRAFFIC.get("runs" if (plan.rel_a is not None and plan.rel_a.d_runs is not None)
-                                                               else "index")) if (world == 1 and args.chi == 4096) else None},
+                              "traffic": (ncu_traffic("k_relayout_segments")
+                                          if (plan.rel_a is not None and plan.rel_a.d_seg is not None) else None)
+                              if (world == 1 and args.chi == 4096) else None},
         "parity": parity,
         "clocks": clocks, "wall_s_timed_region": t_wall,
     }

@@ -145,6 +145,16 @@ def _worker_resident(rank, world, port, q):
 
     ref = [[x.clone() for x in t.Storage] for t in chain()]
     oc = orc.contract_sym(osym(A, seed=41), osym(B, seed=42))
+
+    def svd_chain():
+        """Contract -> Svd_truncate -> Contract -> Contract: the sector SVDs are dealt over the ranks, the factors stay
+        resident, the product U.S.V is rebuilt from them (rank-`keep` approximation of c)."""
+        c = T.Contract(a, b)
+        U, S, V = T.Svd_truncate(c, 120)
+        R = T.Contract(T.Contract(U, S), V)
+        return S, R
+
+    svd_ref = [[x.clone() for x in t.Storage] for t in svd_chain()]
     for tr in ("resident", "pull"):
         parallel.enable(transport=tr)
         for it in range(10):
@@ -158,6 +168,17 @@ def _worker_resident(rank, world, port, q):
                     pl = T._plan.get_contract_plan(c, e)
                     if not getattr(pl, "inherited", False):
                         why.append("resident: ownership was not inherited from the resident operand")
+            if it == 0:
+                S, R = svd_chain()
+                if tr == "resident" and (S._res is None or R._res is None):
+                    why.append("resident: the factors of the sharded Svd_truncate are not resident")
+                for gt, rf in zip(([x.clone() for x in S.Storage], [x.clone() for x in R.Storage]), svd_ref):
+                    if len(gt) != len(rf):
+                        why.append("%s: Svd_truncate kept different sectors" % tr)
+                        continue
+                    for x, y in zip(gt, rf):
+                        den = float(y.abs().max())
+                        err = max(err, float((x - y).abs().max()) / (den if den > 0 else 1.0))
             if it in (0, 9):
                 got = [[x.clone() for x in t.Storage] for t in (c, d, f, g)]   # gathers on demand (every rank)
                 for gt, rf in zip(got, ref):

@@ -24,13 +24,31 @@ import tor10_b200 as T  # noqa: E402
 from helpers import psym  # noqa: E402
 from oracle import tor10_oracle as orc  # noqa: E402  (synthetic-leg generator + host baselines only)
 
-dev = torch.device("cuda", 0)
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if WORLD > 1:       # torchrun: c4 / c5 with sectors sharded over the ranks, results sector-resident (tor10_b200.parallel)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    from tor10_b200 import parallel
+    parallel.enable(transport=os.environ.get("TOR10_GATHER", "resident"))
 flush = torch.empty(256 * 1024 * 1024 // 8, device=dev, dtype=torch.float64)
+
+
+def _max_over_ranks(x):
+    if WORLD == 1:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def timed(fn, n=30, warm=3):
     for _ in range(warm):
         fn()
+    if WORLD > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
     evs = []
     for _ in range(n):
         flush.fill_(1.0)
@@ -40,11 +58,12 @@ def timed(fn, n=30, warm=3):
         e.record()
         evs.append((s, e))
     torch.cuda.synchronize()
-    return float(np.median([s.elapsed_time(e) for s, e in evs]))
+    return _max_over_ranks(float(np.median([s.elapsed_time(e) for s, e in evs])))
 
 
 def emit(**kw):
-    print(json.dumps(kw), flush=True)
+    if RANK == 0:
+        print(json.dumps(dict(kw, n_gpus=WORLD)), flush=True)
 
 
 def c1_itebd(chi=32, steps=300):
@@ -191,15 +210,20 @@ def c4_u1z2(chi=2048):
     pl = T._plan.get_contract_plan(a, b)
     ms = timed(lambda: T.Contract(a, b), n=30)
     th = T.Contract(a, b)
+    T.Svd_truncate(th, chi)                      # (warm: cuSOLVER handles, layouts of the factors)
+    th = T.Contract(a, b)
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     U, S, V = T.Svd_truncate(th, chi)
     torch.cuda.synchronize()
-    svd_s = time.perf_counter() - t0
+    svd_s = _max_over_ranks(time.perf_counter() - t0)
     emit(item="C4 U1xZ2 two-site update chi=%d" % chi, sectors=len(pl.matched), gflop=pl.flops_total / 1e9,
          contract_ms=ms, contract_gflops=pl.flops_total / ms / 1e6, svd_truncate_s=svd_s,
          kept=int(S.bonds[0].dim), updates_per_s_contract_only=1e3 / ms, updates_per_s_with_svd=1.0 / (svd_s + ms * 1e-3),
-         note="Svd_truncate = %d cuSOLVER SVDs (torch default driver), one per sector" % len(th.Storage))
+         note="Svd_truncate = %d sector SVDs (torch / cuSOLVER default driver; one-CTA Jacobi kernel for blocks up to "
+              "64 wide)%s" % (th._layout.nsec, ", dealt over %d ranks by owner (sector-resident)" % WORLD if WORLD > 1 else ""))
 
 
 def c5_peps(D=8, chi=512):
@@ -234,19 +258,22 @@ def c5_peps(D=8, chi=512):
     assert T._plan.STATS == before, "relaunch must replay cached plans"
     plans = [pl for key, pl in T._plan._CONTRACTS.items() if isinstance(pl, T._plan.ContractPlan) and pl.Lo.rank >= 5]
     flops = sum(pl.flops_total for pl in plans)
+    if WORLD > 1:          # (per-rank byte counts below are rank 0's share)
+        torch.cuda.synchronize()
+        dist.barrier()
     # algorithmic bytes: GEMM operands + results, plus read+write of every relayouted operand
     nbytes = sum(8.0 * pl.gemm_bytes + sum(16.0 * r.moved_elems for r in (pl.rel_a, pl.rel_b) if r is not None)
                  for pl in plans)
     emit(item="C5 PEPS double-layer site absorption D=%d chi=%d" % (D, chi), ms=ms, gflop=flops / 1e9,
          gflops=flops / ms / 1e6, algorithmic_GB=nbytes / 1e9, GBs=nbytes / ms / 1e6,
          arithmetic_intensity=flops / nbytes, relayouts=sum((pl.rel_a is not None) + (pl.rel_b is not None) for pl in plans),
-         index_replay=[("runs" if r.d_runs is not None else "index" if r.d_index is not None else "blocks") for pl in plans for r in (pl.rel_a, pl.rel_b) if r is not None],
+         index_replay=[("segments" if r.d_seg is not None else "runs" if r.d_runs is not None else "index" if r.d_index is not None else "blocks") for pl in plans for r in (pl.rel_a, pl.rel_b) if r is not None],
          note="Network.Launch of 3 U1 tensors (2 Contracts + final Permute), plans replayed; contracting over single "
               "D=8 bonds makes this HBM-bound (K <= 64 per sector)")
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["f1", "c3", "c2", "c4", "c5", "c1"]
+    which = sys.argv[1:] or (["c4", "c5"] if WORLD > 1 else ["f1", "c3", "c2", "c4", "c5", "c1"])
     if "c4" in which:
         c4_u1z2()
     if "c5" in which:
@@ -263,3 +290,6 @@ if __name__ == "__main__":
             c1_itebd(chi=64, steps=100)
         except Exception as e:   # large chi: truncated singular values reach 0 and Inverse(lb) fails, as in the reference
             emit(item="C1 iTEBD chi=64", failed=str(e)[:200])
+    if WORLD > 1:
+        dist.barrier()
+        dist.destroy_process_group()

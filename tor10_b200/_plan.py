@@ -960,6 +960,7 @@ class ContractPlan:
                 owner = partition_lpt(cost, world)
             self.sector_owner = owner
             self._own_valid = (np.asarray(owner) == rank) | (np.asarray(owner) < 0)
+            self.matched_all = list(matched)
             matched = [m for m in matched if owner[m[0]] == rank]
         self.matched = matched
         sec_a = sorted(set(m[1] for m in matched))
@@ -1074,6 +1075,13 @@ def _run_resident(self, a, b):
         res = t._res
         if res is None:
             continue
+        if res.slot is None and not res.valid.all():
+            # a resident operand outside peer-readable memory (the factors of a sharded Svd_truncate): when ANY rank
+            # needs a sector it does not hold -- decided from the owner tables, identically on every rank -- the
+            # tensor is completed by a collective; otherwise everybody reads what it has
+            k = 1 if which == "a" else 2
+            if rel is not None or any(int(res.owner[m[k]]) not in (-1, int(self.sector_owner[m[0]])) for m in self.matched_all):
+                parallel.gather_collective(t)
         if res.slot is not None:
             res.slot.last_read = max(res.slot.last_read, seq)
         if rel is None:
@@ -1089,7 +1097,7 @@ def _run_resident(self, a, b):
             need[o] = max(need[o], res.seq)
         rel_args[which] = hit
     pool = rw.pool((self.serial, "out"), self.Lo.arena_elems + ARENA_ALIGN, dt, a.device)
-    slot, war = pool.acquire()
+    slot, war = pool.acquire() if pool is not None else (None, 0)
     need = [max(n, war) if r != rank else 0 for r, n in enumerate(need)]
     rw.wait(need)
     Ap = torch.empty(self.rel_a.packed.size, device=A.device, dtype=dt) if self.rel_a is not None else None
@@ -1103,15 +1111,19 @@ def _run_resident(self, a, b):
         else:
             ptrs = [src.data_ptr()] + [t._res.slot.peer_ptr(o) for o in hit[1]]
             rel.run_segments(ptrs, dst, _lib.dtype_code(dt), seg=hit[0], nseg=int(hit[0].shape[0]))
-    Cc = slot.tensor()
+    Cc = slot.tensor() if slot is not None else self.Lo.new_arena(dt, zero=not self.all_matched)
     self.gemm.run(Ap if Ap is not None else A, Bp if Bp is not None else B, Cc,
                   pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL,
                   signal=(rw.sig_ptrs, seq, rw.done_ctr))
     out = self._make_out(Cc)
     out._res = parallel.Residency(world, rank, self.sector_owner, seq, slot, self._own_valid)
-    slot.holder = weakref.ref(out)
+    if slot is not None:
+        slot.holder = weakref.ref(out)
     if self._transport == "pull":
-        parallel.pull_sectors(out, range(self.Lo.nsec))
+        if slot is not None:
+            parallel.pull_sectors(out, range(self.Lo.nsec))
+        else:
+            parallel.gather_collective(out)
     return out
 
 

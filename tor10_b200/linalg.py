@@ -265,12 +265,39 @@ def _svd_sym(a, keepdim):
     so that Contract(Contract(U, S), V) reproduces (the truncation of) `a`.  The per-sector SVDs run on the
     device through torch/cuSOLVER; only the kept counts come back to the host (they size the new bond)."""
     from .Bond import BD_BRA, BD_KET
-    src = a.Contiguous()
+    from . import parallel
+    shard = parallel.current_shard()
+    sharded = shard is not None and parallel._STATE["transport"] in ("auto", "resident", "pull") \
+        and parallel.transport_for() in ("resident", "pull")
+    if sharded and a._res is not None and a._layout_current():
+        src = a                                  # a sector-resident Contract result: every rank factorises what it owns
+    else:
+        src = a.Contiguous()
     L = src._layout
-    views = L.views(src._arena_tensor())
     drv = os.environ.get("TOR10_SVD_DRIVER") if src.device.type == "cuda" else None
-    fac = [torch.linalg.svd(v, full_matrices=False, driver=drv or None) for v in views]
-    counts = [int(f[1].numel()) for f in fac]
+    owner = None
+    if sharded:
+        # independent sector SVDs are dealt over the ranks (SURVEY 8e): a resident operand keeps its owners, a
+        # replicated one is split by LPT on the SVD cost m n min(m, n)
+        rank, world = shard
+        if src._res is not None:
+            owner = np.asarray(src._res.owner).copy()
+            free = owner < 0
+            owner[free] = np.arange(int(free.sum())) % world        # zero sectors: anybody
+        else:
+            cost = L.rows.astype(np.float64) * L.cols * np.minimum(L.rows, L.cols)
+            owner = parallel.partition_lpt(cost, world)
+        views = L.views(src._arena_tensor(resident_ok=True))
+        mine = [i for i in range(L.nsec) if owner[i] == rank]
+    else:
+        views = L.views(src._arena_tensor())
+        mine = list(range(L.nsec))
+
+    def one(v):
+        small = _svd_small(v) if _SVD_SMALL else None
+        return small if small is not None else torch.linalg.svd(v, full_matrices=False, driver=drv or None)
+    fac = {i: one(views[i]) for i in mine}
+    counts = [int(min(L.rows[i], L.cols[i])) for i in range(L.nsec)]
     total = sum(counts)
     if keepdim is None:
         keep = counts
@@ -278,7 +305,16 @@ def _svd_sym(a, keepdim):
         if keepdim <= 0 or keepdim > total:
             raise ValueError("Svd_truncate", "[ERROR] the keepdim=%d is invalid, must larger than 0 and smaller than "
                                              "the total number of eigenvalues." % keepdim)
-        all_s = torch.cat([f[1] for f in fac])
+        if sharded:
+            # every rank contributes the singular values of its sectors; one small all-reduce completes the list
+            import torch.distributed as dist
+            starts = np.concatenate([[0], np.cumsum(counts)])
+            all_s = torch.zeros(total, device=src.device, dtype=src.dtype)
+            for i in mine:
+                all_s[int(starts[i]):int(starts[i + 1])] = fac[i][1]
+            dist.all_reduce(all_s, group=parallel._STATE["group"])
+        else:
+            all_s = torch.cat([fac[i][1] for i in range(L.nsec)])
         sec_id = torch.cat([torch.full((c,), i, dtype=torch.int64, device=all_s.device) for i, c in enumerate(counts)])
         top = torch.topk(all_s, keepdim).indices
         keep = torch.bincount(sec_id[top], minlength=len(counts)).cpu().tolist()   # prefix of every sector
@@ -297,12 +333,23 @@ def _svd_sym(a, keepdim):
     V = UniTensor(bonds=[xk] + list(src.bonds[rr:]), rowrank=1, labels=[tmp - 2] + list(src.labels[rr:]),
                   device=dev, dtype=dt)
     uv, sv, vv = (t._layout.views(t._arena) for t in (U, S, V))
+    own = [np.full(t._layout.nsec, -1, dtype=np.int64) for t in (U, S, V)] if sharded else None
     for i, k in kept:
         q = L.block_qnums[i]
+        if sharded:
+            for j, t in enumerate((U, S, V)):
+                own[j][t._layout.sector_of(q)] = owner[i]
+        if i not in fac:
+            continue
         u, s_, vh = fac[i]
         uv[U._layout.sector_of(q)].copy_(u[:, :k])
         sv[S._layout.sector_of(q)].copy_(torch.diag(s_[:k]))
         vv[V._layout.sector_of(q)].copy_(vh[:k, :])
+    if sharded:
+        # the factors stay sector-resident: every rank holds the sectors it factorised (not in peer-readable memory:
+        # a consumer that needs foreign sectors completes them by a collective, parallel.gather_collective)
+        for j, t in enumerate((U, S, V)):
+            t._res = parallel.Residency(shard[1], shard[0], own[j], 0, None)
     return U, S, V
 
 

@@ -336,15 +336,17 @@ class ArenaPool:
         self.rw, self.n, self.dtype = rw, int(n), dtype
         self.stride = (self.n + 63) // 64 * 64
         esz = torch.empty(0, dtype=dtype).element_size()
-        whole = symm_mem.empty(POOL_DEPTH * self.stride, dtype=dtype, device=device)
+        depth = POOL_DEPTH if self.stride * esz <= (256 << 20) else 2     # large results: two slots
+        self.depth = depth
+        whole = symm_mem.empty(depth * self.stride, dtype=dtype, device=device)
         whole.zero_()
         torch.cuda.synchronize(device)
         hdl = symm_mem.rendezvous(whole, group=rw.group_or_world())
         self.whole, self.hdl = whole, hdl
-        self.bufs = [whole[k * self.stride:k * self.stride + self.n] for k in range(POOL_DEPTH)]
-        base = [int(hdl.get_buffer(r, (POOL_DEPTH * self.stride,), dtype).data_ptr()) for r in range(rw.world)]
-        self.peer_ptrs = [[base[r] + k * self.stride * esz for r in range(rw.world)] for k in range(POOL_DEPTH)]
-        self.slots = [_Slot(self, k) for k in range(POOL_DEPTH)]
+        self.bufs = [whole[k * self.stride:k * self.stride + self.n] for k in range(depth)]
+        base = [int(hdl.get_buffer(r, (depth * self.stride,), dtype).data_ptr()) for r in range(rw.world)]
+        self.peer_ptrs = [[base[r] + k * self.stride * esz for r in range(rw.world)] for k in range(depth)]
+        self.slots = [_Slot(self, k) for k in range(depth)]
         self.turn = 0
         dist.barrier(group=rw.group)
 
@@ -352,7 +354,7 @@ class ArenaPool:
         """Next slot of the ring.  A tensor still living in it is gathered out first (every rank does so at the
         same program point).  Returns (slot, write-after-read bound)."""
         slot = self.slots[self.turn]
-        self.turn = (self.turn + 1) % POOL_DEPTH
+        self.turn = (self.turn + 1) % self.depth
         old = slot.holder() if slot.holder is not None else None
         if old is not None and getattr(old, "_res", None) is not None and old._res.slot is slot:
             old._materialize()
@@ -417,9 +419,18 @@ class ResidentWorld:
         _lib.check(_lib.load().t10_signal_flags(1, self.sig_ptrs, int(value), _lib.stream_ptr()))
 
     def pool(self, key, n, dtype, device):
-        p = self.pools.get(key)
-        if p is None:
-            p = ArenaPool(self, n, dtype, device)
+        """The plan's ring of symmetric result arenas, or None when symmetric memory of that size cannot be had (the
+        plan's results then live in private memory: still sector-resident, completed by a collective on demand)."""
+        p = self.pools.get(key, False)
+        if p is False:
+            try:
+                p = ArenaPool(self, n, dtype, device)
+            except RuntimeError:
+                p = None
+            ok = torch.tensor([1 if p is not None else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)        # every rank takes the same decision
+            if int(ok.item()) == 0:
+                p = None
             self.pools[key] = p
         return p
 
@@ -494,6 +505,33 @@ def pull_sectors(t, needed):
     res.slot.last_read = max(res.slot.last_read, rw.seq + 1)
 
 
+def gather_collective(t):
+    """Complete a resident tensor that does NOT live in peer-readable memory (results assembled by torch ops, e.g. the
+    factors of a sharded Svd_truncate): one broadcast per owner and contiguous run of its sectors.  A collective:
+    every rank must call it at the same program point."""
+    res = t._res
+    group = _STATE["group"]
+    arena = t._arena
+    L = t._layout
+    run_owner, run_lo, run_hi = None, 0, 0
+    runs = []
+    for s in range(len(res.owner)):
+        o = int(res.owner[s])
+        lo = int(L.arena_off[s])
+        hi = lo + int(L.rows[s]) * int(L.ld[s])
+        if o == run_owner and o >= 0:
+            run_hi = hi
+        else:
+            if run_owner is not None and run_owner >= 0:
+                runs.append((run_owner, run_lo, run_hi))
+            run_owner, run_lo, run_hi = o, lo, hi
+    if run_owner is not None and run_owner >= 0:
+        runs.append((run_owner, run_lo, run_hi))
+    for o, lo, hi in runs:
+        dist.broadcast(arena[lo:hi], src=dist.get_global_rank(group, o) if group is not None else o, group=group)
+    res.valid[:] = True
+
+
 def materialize(t):
     """Gather a resident tensor on demand: pull every foreign sector, publish the read (so the owners may reuse
     their slots), move the tensor into private memory.  Every rank that holds the tensor must call this at the
@@ -510,7 +548,7 @@ def materialize(t):
         t._arena = t._arena.clone()
         if res.slot.holder is not None and res.slot.holder() is t:
             res.slot.holder = None
-    elif not res.valid.all():
-        raise RuntimeError("tor10_b200.parallel: resident tensor is incomplete and its peers' memory is gone")
+    elif res.world > 1:
+        gather_collective(t)
     t._res = None
     t._blocks = None
