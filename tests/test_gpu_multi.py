@@ -155,6 +155,27 @@ def _worker_resident(rank, world, port, q):
         return S, R
 
     svd_ref = [[x.clone() for x in t.Storage] for t in svd_chain()]
+
+    # config-5 shape: a Network of U1 tensors (E1 - P - E2), launched twice; the intermediate stays resident
+    u1 = [["U1", 0]]
+    dq = sorted([[1], [0], [-1]], reverse=True)
+    cq = sorted(orc.gauss_u1_qnums(12, -1, 1, 0.8).tolist(), reverse=True)
+
+    def bd(dim, bt, qn):
+        return {"dim": dim, "btype": bt, "qnums": qn, "syms": u1}
+    nspecs = {"E1": {"bonds": [bd(12, -1, cq), bd(3, 1, dq), bd(12, 1, cq)], "rowrank": 1, "labels": [0, 1, 2]},
+              "P": {"bonds": [bd(3, -1, dq), bd(3, -1, dq), bd(3, 1, dq), bd(3, 1, dq)], "rowrank": 2, "labels": [0, 1, 2, 3]},
+              "E2": {"bonds": [bd(12, -1, cq), bd(3, -1, dq), bd(12, 1, cq)], "rowrank": 2, "labels": [0, 1, 2]}}
+    net = T.Network()
+    net.Fromstring("E1: 10; 11 12\nP: 11 20; 21 13\nE2: 12 13; 14\nTOUT: 10 20; 21 14\nOrder: (E1,P),E2\n")
+    for i, (k, sp) in enumerate(nspecs.items()):
+        net.Put(k, psym(T, sp, seed=600 + i, device=dev))
+
+    def launch():
+        net.Launch()
+        return net.Launch().Contiguous()
+
+    net_ref = [x.clone() for x in launch().Storage]
     for tr in ("resident", "pull"):
         parallel.enable(transport=tr)
         for it in range(10):
@@ -179,6 +200,10 @@ def _worker_resident(rank, world, port, q):
                     for x, y in zip(gt, rf):
                         den = float(y.abs().max())
                         err = max(err, float((x - y).abs().max()) / (den if den > 0 else 1.0))
+            if it == 0:
+                for x, y in zip(launch().Storage, net_ref):
+                    den = float(y.abs().max())
+                    err = max(err, float((x - y).abs().max()) / (den if den > 0 else 1.0))
             if it in (0, 9):
                 got = [[x.clone() for x in t.Storage] for t in (c, d, f, g)]   # gathers on demand (every rank)
                 for gt, rf in zip(got, ref):
