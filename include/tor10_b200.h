@@ -317,7 +317,8 @@ int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t n, const vo
  * (n' = n rounded up to even; t10_svd_small_limits); element (r, c) of matrix i is d_A[a_off + r * row_stride +
  * c * col_stride] (a wide matrix is passed transposed through its strides).  Writes U [m, n] row-major at
  * d_U + u_off, the singular values, descending, at d_S + s_off and Vh [n, n] row-major at d_Vh + v_off, so that
- * A = U diag(S) Vh.  A zero singular value gets a zero U column.  d_info[i] (may be NULL): bit 0 = matrix i was still
+ * A = U diag(S) Vh.  A zero singular value gets a zero U column; columns below m eps ||A||_F (the numerical null
+ * space) are left as they are: their U columns are not orthonormalised.  d_info[i] (may be NULL): bit 0 = matrix i was still
  * rotating after 40 sweeps, bits 1.. = sweeps run.  d_W (may be NULL) + w_off >= 0: warm-start state of the matrix,
  * T10_SVD_WARM_ELEMS(n) elements, zero-initialised by the caller and then left to the kernel -- a ring of two slots
  * used in turn, each keeping the right singular vectors of the call before last on this state, from which the

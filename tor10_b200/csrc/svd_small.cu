@@ -9,6 +9,7 @@
 // the factors are written out sorted.  Same accuracy class as LAPACK's dgesvj (columns are orthogonalised until no
 // pair has |a_p . a_q| > m eps |a_p| |a_q|).  Larger matrices stay on torch / cuSOLVER.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -39,9 +40,10 @@ constexpr int SV_LPP = 8;             // lanes per column pair: four pairs share
 template <typename T>
 __global__ void __launch_bounds__(SV_LPP * SV_MAX_N / 2, 1)
 k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __restrict__ Vh, T* __restrict__ W,
-            const __grid_constant__ SvdBatch batch, int* __restrict__ info) {
+            const __grid_constant__ SvdBatch batch, int* __restrict__ info, double abs_kappa) {
   extern __shared__ __align__(16) unsigned char sv_raw[];
   __shared__ int s_rot;
+  __shared__ unsigned s_maxr;          // largest squared |cos| of a rotated pair in this sweep (float bits)
   __shared__ T s_f2;
   __shared__ T s_sig[SV_MAX_N];
   __shared__ int s_rank[SV_MAX_N];
@@ -115,10 +117,12 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
   const T tol = eps * (T)m;                 // |a_p . a_q| <= m eps |a_p| |a_q| counts as orthogonal (rounding floor of
   const T tol2 = tol * tol;                 // the dot product itself is ~sqrt(m) eps: a tighter bound never settles)
   // Columns whose norm is below m eps ||A||_F are rounding noise of the larger ones (the numerical null space of a
-  // rank-deficient or fast-decaying matrix -- every iTEBD step produces one).  Their directions carry no
-  // information; orthogonalising them to full precision never settles (each rotation against a large column
-  // re-randomises them at its rounding level).  Pairs that involve such a column are held to sqrt(eps) only: the
-  // null-space basis still comes out orthonormal to ~1e-8, the sweeps are spent on the columns that matter.
+  // rank-deficient or fast-decaying matrix -- every iTEBD step produces one: 32 of its 64 columns).  Their
+  // directions carry no information and are re-randomised by every call's rounding; orthogonalising them costs most
+  // of the sweeps and never settles.  A pair that involves such a column is left alone: the column contributes less
+  // than m eps ||A||_F to A = U S Vh whatever its direction, V stays orthogonal (a product of rotations), and the
+  // triplets of the columns that matter are unaffected to that level.  (U columns of such singular values are
+  // therefore not orthonormal -- LAPACK returns an arbitrary orthonormal completion there.)
   if (tid == 0) s_f2 = T(0);
   __syncthreads();
   {
@@ -133,7 +137,11 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
   }
   __syncthreads();
   const T floor2 = tol2 * s_f2;             // squared norm below which a column counts as noise
-  const T loose2 = eps;                     // (sqrt(eps))^2
+  // ... and a pair whose inner product is below eps ||A||_F^2 in ABSOLUTE terms is left alone as well: what it
+  // leaves perturbs singular values by less than eps ||A|| -- the normwise accuracy of LAPACK's dgesdd / cuSOLVER.
+  // (The purely relative test would keep polishing the tiny triplets of a graded matrix, whose directions a 1e-6
+  // change of A scrambles anyway: 8-10 sweeps per iTEBD step even from a warm start.)
+  const T abs2 = (eps * (T)abs_kappa * s_f2) * (eps * (T)abs_kappa * s_f2);
   const int npairs = ne / 2, nrounds = ne - 1;
 #ifdef T10_SVD_DEBUG
   const long long dbg_c0 = clock64();
@@ -142,7 +150,7 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
 #endif
   int sweep = 0;
   for (; sweep < SV_MAX_SWEEPS; ++sweep) {
-    if (tid == 0) s_rot = 0;
+    if (tid == 0) { s_rot = 0; s_maxr = 0u; }
     __syncthreads();
     for (int round = 0; round < nrounds; ++round) {
       for (int k = grp; k < npairs; k += ngrp) {
@@ -163,7 +171,7 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
           beta += __shfl_xor_sync(gmask, beta, o);
           gamma += __shfl_xor_sync(gmask, gamma, o);
         }
-        if (gamma * gamma > (fmin(alpha, beta) < floor2 ? loose2 : tol2) * alpha * beta) {
+        if (fmin(alpha, beta) >= floor2 && gamma * gamma > fmax(tol2 * alpha * beta, abs2)) {
           // Rotation: t = tan(theta) only has to be CLOSE to the annihilating tangent (what it leaves is removed by
           // the next sweep), so it is computed in fast fp32 arithmetic on operands scaled into range -- an fp64
           // divide or square root is a ~30-instruction dependent chain and the exact formula needs three of each.
@@ -207,12 +215,21 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
             vp[r] = c * x - s * y;
             vq[r] = s * x + c * y;
           }
-          if (sub == 0) s_rot = 1;
+          if (sub == 0) {
+            s_rot = 1;
+            const float abf = (float)(alpha * scale) * (float)(beta * scale);
+            const float r2 = abf > 0.0f ? fminf(__fdividef(0.25f * gf * gf, abf), 1.0f) : 1.0f;
+            atomicMax(&s_maxr, __float_as_uint(r2));
+          }
         }
       }
       __syncthreads();
     }
-    if (s_rot == 0) break;
+    // converged: nothing rotated -- or everything that did was already orthogonal to sqrt-of-tolerance level: what a
+    // rotation with an fp32 tangent leaves is ~1e-7 of what it found (plus second-order terms), so after a sweep whose
+    // largest |cos| was below 1e-8 (1e-4 in fp32) every pair is below the tolerance and the checking sweep is skipped
+    const float done_below = sizeof(T) == 8 ? 1e-16f : 1e-8f;
+    if (s_rot == 0 || __uint_as_float(s_maxr) < done_below) break;
     __syncthreads();
   }
 #ifdef T10_SVD_DEBUG
@@ -285,6 +302,12 @@ extern "C" int t10_svd_small(int dtype, int64_t nprob, const int64_t* h_prob, co
     T10_CUDA(cudaFuncSetAttribute(k_svd_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
+  // absolute floor of the rotation test, in units of eps ||A||_F^2 (TOR10_SVD_ABS; 0 = purely relative test)
+  static double kappa = -1.0;
+  if (kappa < 0.0) {
+    const char* e = getenv("TOR10_SVD_ABS");
+    kappa = e ? atof(e) : 1e-4;
+  }
   for (int64_t base = 0; base < nprob; base += SV_BATCH) {
     const int cnt = (int)std::min<int64_t>(SV_BATCH, nprob - base);
     SvdBatch b;
@@ -316,10 +339,10 @@ extern "C" int t10_svd_small(int dtype, int64_t nprob, const int64_t* h_prob, co
     int* info = d_info ? d_info + base : nullptr;
     if (dtype == T10_F64)
       k_svd_small<double><<<(unsigned)cnt, threads, smem, st>>>((const double*)d_A, (double*)d_U, (double*)d_S,
-                                                               (double*)d_Vh, (double*)d_W, b, info);
+                                                               (double*)d_Vh, (double*)d_W, b, info, kappa);
     else
       k_svd_small<float><<<(unsigned)cnt, threads, smem, st>>>((const float*)d_A, (float*)d_U, (float*)d_S,
-                                                              (float*)d_Vh, (float*)d_W, b, info);
+                                                              (float*)d_Vh, (float*)d_W, b, info, kappa);
     T10_LAUNCH_CHECK();
   }
   return T10_OK;

@@ -183,6 +183,7 @@ _SVD_SMALL = os.environ.get("TOR10_SVD_SMALL", "1") == "1"
 _SVD_LIMITS = []
 _SVD_WARM = os.environ.get("TOR10_SVD_WARM", "1") == "1"
 _SVD_STATE = {}
+_SVD_DEBUG = []          # [int32 device word, list]: set by tools/svd_sweeps.py
 
 
 def _svd_small(x):
@@ -222,7 +223,9 @@ def _svd_small(x):
     with _lib.on_device(x.device):
         _lib.check(_lib.load().t10_svd_small(_lib.dtype_code(x.dtype), 1, prob, x.data_ptr(), u.data_ptr(),
                                              s.data_ptr(), vh.data_ptr(), W.data_ptr() if W is not None else None,
-                                             None, _lib.stream_ptr()))
+                                             _SVD_DEBUG[0].data_ptr() if _SVD_DEBUG else None, _lib.stream_ptr()))
+    if _SVD_DEBUG:          # tools/svd_sweeps.py: sweeps per call (synchronises)
+        _SVD_DEBUG[1].append(int(_SVD_DEBUG[0].item()) >> 1)
     if wide:          # A^T = u s vh  =>  A = vh^T s u^T
         return vh.t(), s, u.t()
     return u, s, vh
