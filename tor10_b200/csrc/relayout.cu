@@ -217,7 +217,7 @@ k_relayout_runs(const T* __restrict__ src, T* __restrict__ dst, int64_t n, const
 // multi-GPU run the pieces owned by another rank are read through that rank's NVLink peer mapping, so the
 // exchange a relayout of a sharded tensor needs is part of the copy itself (no collective, no staging).
 // src < 0: zero fill.  The kernel opens the programmatic launch window of the GEMM that follows it.
-constexpr int RS_THREADS = 256, RS_MAXLEN = 256, RS_MAXSRC = 8;
+constexpr int RS_THREADS = 512, RS_MAXLEN = 256, RS_MAXSRC = 8;
 struct SegSources { const void* base[RS_MAXSRC]; };
 template <typename T>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -226,23 +226,30 @@ k_relayout_segments(const __grid_constant__ SegSources srcs, T* __restrict__ dst
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * (RS_THREADS / 32);
-  for (int s = (blockIdx.x * RS_THREADS + threadIdx.x) >> 5; s < nseg; s += nwarps) {
-    const int4 d = __ldg(seg + s);                      // {dst, src, len, source}
+  int s = (blockIdx.x * RS_THREADS + threadIdx.x) >> 5;
+  if (s >= nseg) return;
+  int4 d = __ldg(seg + s);                              // {dst, src, len, source}
+  for (; s < nseg; s += nwarps) {
+    // the next descriptor is in flight while this segment's data moves (one round trip less per segment)
+    const int sn = s + nwarps;
+    int4 dn = d;
+    if (sn < nseg) dn = __ldg(seg + sn);
     T* o = dst + d.x;
     if (d.y < 0) {
 #pragma unroll
       for (int u = 0; u < RS_MAXLEN / 32; ++u)
         if (lane + 32 * u < d.z) o[lane + 32 * u] = T(0);
-      continue;
+    } else {
+      const T* in = reinterpret_cast<const T*>(srcs.base[d.w]) + d.y;
+      T v[RS_MAXLEN / 32];
+#pragma unroll
+      for (int u = 0; u < RS_MAXLEN / 32; ++u)
+        if (lane + 32 * u < d.z) v[u] = in[lane + 32 * u];
+#pragma unroll
+      for (int u = 0; u < RS_MAXLEN / 32; ++u)
+        if (lane + 32 * u < d.z) o[lane + 32 * u] = v[u];
     }
-    const T* in = reinterpret_cast<const T*>(srcs.base[d.w]) + d.y;
-    T v[RS_MAXLEN / 32];
-#pragma unroll
-    for (int u = 0; u < RS_MAXLEN / 32; ++u)
-      if (lane + 32 * u < d.z) v[u] = in[lane + 32 * u];
-#pragma unroll
-    for (int u = 0; u < RS_MAXLEN / 32; ++u)
-      if (lane + 32 * u < d.z) o[lane + 32 * u] = v[u];
+    d = dn;
   }
 }
 
@@ -532,10 +539,10 @@ extern "C" int t10_relayout_segments(int dtype, int nsrc, const void* const* h_s
   memset(&ss, 0, sizeof(ss));
   for (int i = 0; i < nsrc; ++i) ss.base[i] = h_src[i];
   const int64_t warps = nseg;
-  static int rs_ctas = 0;        // CTAs per SM (TOR10_RELAYOUT_SEG_CTAS, default 6 = the register limit)
+  static int rs_ctas = 0;        // CTAs of 512 threads per SM (TOR10_RELAYOUT_SEG_CTAS, default 3: 48 warps per SM)
   if (rs_ctas == 0) {
     const char* e = getenv("TOR10_RELAYOUT_SEG_CTAS");
-    rs_ctas = e ? std::max(1, std::min(8, atoi(e))) : 6;
+    rs_ctas = e ? std::max(1, std::min(8, atoi(e))) : 3;
   }
   unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(warps, RS_THREADS / 32), (int64_t)sm_count() * rs_ctas));
   if (dtype == T10_F64)
