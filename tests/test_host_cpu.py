@@ -352,3 +352,98 @@ def test_sector_gather_world2_gloo(T):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert res[0][2] == res[1][2] == [0, 2, 4]
+
+
+# ---- round 2: bounded plan caches, sector-resident ownership logic (pure host code) ----------------------------
+def test_plan_cache_is_a_bounded_lru(T):
+    from tor10_b200 import _plan
+
+    class P:
+        def __init__(self, nbytes):
+            self.nbytes = nbytes
+
+        def plan_bytes(self):
+            return self.nbytes
+    c = _plan.LRU(3)
+    for k in range(5):
+        c[k] = P(10)
+    assert len(c) == 3 and c.get(0) is None and c.get(1) is None and c.get(4) is not None and c.evicted == 2
+    c.get(2)                       # touched: 3 is now the oldest
+    c[5] = P(10)
+    assert c.get(3) is None and c.get(2) is not None
+    b = _plan.LRU(100, max_bytes=25)
+    b["a"], b["b"], b["c"] = P(10), P(10), P(10)       # 30 bytes: the oldest goes
+    assert b.get("a") is None and b.bytes == 20
+    b["big"] = P(1000)                                  # a single entry over the budget is kept (it is in use)
+    assert len(b) == 1 and b.get("big") is not None
+
+
+def test_resident_ownership_and_fetch_plan(T):
+    """Ownership propagates from a resident first operand; a rank pulls exactly the needed sectors it does
+    not hold, grouped by owner, as whole 16-byte vectors."""
+    from tor10_b200 import parallel
+    a_owner = np.array([0, 1, -1, 1, 0])
+    matched = [(0, 4, 0), (1, 0, 1), (3, 1, 2), (4, 2, 3)]            # (out sector, A sector, B sector)
+    own = parallel.inherit_owner(a_owner, matched, 6, None, 2)
+    assert own.tolist() == [0, 0, -1, 1, -1, -1]                     # out 4 pairs with a zero A sector: nobody's
+    res0 = parallel.Residency(2, 0, own, 7, None)
+    assert res0.valid.tolist() == [True, True, True, False, True, True]
+
+    class L:
+        arena_off = np.array([0, 16, 48, 64, 96, 112])
+        rows = np.array([2, 4, 1, 3, 1, 1])
+        ld = np.array([4, 6, 2, 6, 2, 2])
+    plan = parallel.fetch_plan(L, res0, [0, 3, 5])
+    assert plan == {1: [(64, 84)]}                                    # 3 * 6 = 18 elements -> 20 (whole vectors)
+    res1 = parallel.Residency(2, 1, own, 7, None)
+    assert parallel.fetch_plan(L, res1, [0, 1, 3]) == {0: [(0, 8), (16, 40)]}
+    assert res0.key() == res1.key()                                   # the plan key does not depend on the rank
+
+
+def _collective_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tor10_b200 import parallel
+    parallel.enable()
+
+    class L:
+        arena_off = np.array([0, 16, 48, 64])
+        rows = np.array([2, 4, 2, 4])
+        ld = np.array([8, 8, 8, 8])
+        nsec = 4
+
+    class Tn:      # the three fields gather_collective touches
+        pass
+    t = Tn()
+    t._layout = L
+    owner = np.array([0, 0, 1, -1])
+    t._res = parallel.Residency(world, rank, owner, 0, None)
+    t._arena = torch.zeros(96 + 16, dtype=torch.float64)
+    for s_ in range(4):
+        if owner[s_] == rank:
+            lo = int(L.arena_off[s_])
+            t._arena[lo:lo + int(L.rows[s_] * L.ld[s_])] = 10.0 * (rank + 1) + s_
+    parallel.gather_collective(t)
+    want = torch.zeros_like(t._arena)
+    for s_ in range(4):
+        if owner[s_] >= 0:
+            lo = int(L.arena_off[s_])
+            want[lo:lo + int(L.rows[s_] * L.ld[s_])] = 10.0 * (owner[s_] + 1) + s_
+    q.put((rank, bool(torch.equal(t._arena, want)) and bool(t._res.valid.all())))
+    dist.destroy_process_group()
+
+
+def test_resident_collective_completion_world2_gloo(T):
+    """A resident tensor outside peer-readable memory is completed by one broadcast per owner run (the N > 1 path of
+    the sharded Svd_truncate's factors), here over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_collective_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

@@ -11,7 +11,7 @@ import numpy as np
 import torch  # noqa: F401  (loads libcudart / creates the CUDA context the kernels run in)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libtor10_b200.so")
+LIB_PATH = os.environ.get("TOR10_LIB") or os.path.join(HERE, "lib", "libtor10_b200.so")   # (TOR10_LIB: debug builds)
 
 T10_F64, T10_F32 = 0, 1
 T10_SYM_U1, T10_SYM_ZN = 0, 1

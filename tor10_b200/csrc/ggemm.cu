@@ -1024,7 +1024,8 @@ static int launch_f64(bool launch, int* nslots_out, const double* A, const doubl
   constexpr int PEER_TILE_BYTES = Cfg::BM * (Cfg::BN + 2) * 8;   // staging tile of the fused all-gather
   constexpr bool PEER_FITS = Cfg::SMEM_BYTES + PEER_TILE_BYTES <= 227 * 1024;
   T10_REQUIRE(peers.n == 0 || PEER_FITS, T10_ERR_UNSUPPORTED, "fused all-gather: tile configuration too large");
-  static int ctas_per_sm = 0;
+  static int ctas_by_dev[T10_MAX_DEVICES] = {0};
+  int& ctas_per_sm = ctas_by_dev[cur_device()];
   if (ctas_per_sm == 0) {
     T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES + (PEER_FITS ? PEER_TILE_BYTES : 0)));
@@ -1063,7 +1064,8 @@ static int launch_f64_v5(bool launch, int* nslots_out, const double* A, const do
   constexpr int PEER_TILE_BYTES = Cfg::BM * (Cfg::BN + 2) * 8;   // staging tile of the fused all-gather
   constexpr bool PEER_FITS = Cfg::SMEM_BYTES + PEER_TILE_BYTES <= 227 * 1024;
   T10_REQUIRE(peers.n == 0 || PEER_FITS, T10_ERR_UNSUPPORTED, "fused all-gather: tile configuration too large");
-  static int ctas_per_sm = 0;
+  static int ctas_by_dev[T10_MAX_DEVICES] = {0};
+  int& ctas_per_sm = ctas_by_dev[cur_device()];
   if (ctas_per_sm == 0) {
     T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::SMEM_BYTES + (PEER_FITS ? PEER_TILE_BYTES : 0)));
@@ -1095,7 +1097,8 @@ static int launch_f64_mixed(bool launch, int* nslots_out, const double* A, const
                             const t10_gemm_problem* prob, int64_t ntiles, const int32_t* tiles, int64_t nslots,
                             const int32_t* slot_start, int32_t* /*sched*/, cudaStream_t st, const PeerOut& peers) {
   auto kern = k_ggemm_f64_mixed<2>;
-  static int ctas_per_sm = 0;
+  static int ctas_by_dev[T10_MAX_DEVICES] = {0};
+  int& ctas_per_sm = ctas_by_dev[cur_device()];
   if (ctas_per_sm == 0) {
     T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_BYTES));
     int occ = 0;
@@ -1359,7 +1362,8 @@ static int launch_streamk(const void* d_A, const void* d_B, void* d_C, int64_t n
   T10_REQUIRE(((uintptr_t)d_A & 15) == 0 && ((uintptr_t)d_B & 15) == 0, T10_ERR_INVALID,
               "ggemm_streamk: operand base pointers must be 16-byte aligned");
   auto kern = k_ggemm_f64_mixed_sk<2>;
-  static int resident = 0;
+  static int resident_by_dev[T10_MAX_DEVICES] = {0};
+  int& resident = resident_by_dev[cur_device()];
   if (resident == 0) {
     T10_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MIX_SMEM_BYTES));
     int occ = 0;

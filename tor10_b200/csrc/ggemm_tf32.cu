@@ -313,16 +313,15 @@ k_ggemm_tf32x3(const float* __restrict__ Abase, const float* __restrict__ Bbase,
   }
 }
 
-static int* d_err = nullptr;
+static int* d_err_by_dev[T10_MAX_DEVICES] = {nullptr};    // error words, one per device
 
 int launch_ggemm_tf32x3(const float* A, const float* B, float* C, const t10_gemm_problem* prob, int64_t ntiles,
                         const int32_t* tiles, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  int*& d_err = d_err_by_dev[cur_device()];
+  if (d_err == nullptr) {
     T10_CUDA(cudaFuncSetAttribute(k_ggemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM));
     T10_CUDA(cudaMalloc(&d_err, 4 * sizeof(int)));
     T10_CUDA(cudaMemset(d_err, 0, 4 * sizeof(int)));
-    attr = true;
   }
   unsigned grid = (unsigned)std::min<int64_t>(ntiles, (int64_t)sm_count());
   k_ggemm_tf32x3<<<grid, TF_THREADS, TF_SMEM, st>>>(A, B, C, prob, ntiles, (const int4*)tiles, d_err);
@@ -335,7 +334,8 @@ int launch_ggemm_tf32x3(const float* A, const float* B, float* C, const t10_gemm
 // 1 if any CTA of any tcgen05 launch so far gave up waiting on an MMA barrier (never on a healthy run)
 extern "C" int t10_ggemm_tf32_status(int* h_flag) {
   *h_flag = 0;
-  if (t10::d_err == nullptr) return T10_OK;
-  T10_CUDA(cudaMemcpy(h_flag, t10::d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  int* d_err = t10::d_err_by_dev[t10::cur_device()];
+  if (d_err == nullptr) return T10_OK;
+  T10_CUDA(cudaMemcpy(h_flag, d_err, sizeof(int), cudaMemcpyDeviceToHost));
   return T10_OK;
 }

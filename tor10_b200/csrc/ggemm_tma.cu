@@ -106,6 +106,11 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
   const unsigned full0 = tg_smem(&bars[0]), empty0 = tg_smem(&bars[TG_STAGES]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+#ifdef T10_TRACE_PHASES
+  unsigned long long ph_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ph_entry));
+#endif
+  const int t_beg = slot_start[blockIdx.x], t_end = slot_start[blockIdx.x + 1];   // (in flight across the set-up)
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < TG_STAGES; ++s) {
@@ -115,7 +120,6 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  const int t_beg = slot_start[blockIdx.x], t_end = slot_start[blockIdx.x + 1];
 
   if (warp == 4) {
     // ------------------------------------------------------------------ producer ----
@@ -234,12 +238,21 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
       if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(sk_flags + pslot), "r"(sk_epoch) : "memory");
+#ifdef T10_TRACE_PHASES
+        if (trace != nullptr) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          trace[4 * t + 0] = now;
+          trace[4 * t + 1] = ph_entry;
+        }
+#endif
       }
       continue;
     }
     if (nfix > 0) {
-      if (threadIdx.x == 0) {
-        for (int f = 0; f < nfix; ++f) {
+      if (warp == 0) {
+        // one lane per parked slot: the flags are polled side by side (one L2 round trip instead of nfix)
+        for (int f = lane; f < nfix; f += 32) {
           int v = sk_epoch - 1;
           for (int spin = 0; spin < (1 << 22); ++spin) {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(sk_flags + ffix + f) : "memory");
@@ -251,6 +264,7 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
       }
       tg_consumer_sync();
       if (active) {
+#pragma unroll 2
         for (int f = 0; f < nfix; ++f) {
           const double2* w = reinterpret_cast<const double2*>(sk_ws + (int64_t)(ffix + f) * (128 * 34)) + threadIdx.x;
 #pragma unroll
@@ -264,6 +278,14 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
         }
       }
     }
+#ifdef T10_TRACE_PHASES
+    if (trace != nullptr && threadIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      trace[4 * t + 0] = now;            // fix-up done (stores follow)
+      trace[4 * t + 1] = ph_entry;
+    }
+#endif
     if (!active) continue;
     const t10_gemm_problem p = prob[tile.x];
     const int m_end = m0 + m_rem, n_end = n0 + n_rem;

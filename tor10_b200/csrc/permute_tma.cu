@@ -194,7 +194,8 @@ int permute_dense_tma(int dtype, const void* src, void* dst, int rank, const int
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return T10_ERR_UNSUPPORTED;  // e.g. overlapping-stride views
 
-  static bool attr_set = false;
+  static bool attr_by_dev[T10_MAX_DEVICES] = {false};
+  bool& attr_set = attr_by_dev[cur_device()];
   const int smem = TMA_STAGES * TMA_TILE_BYTES;
   if (!attr_set) {
     T10_CUDA(cudaFuncSetAttribute(k_permute_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

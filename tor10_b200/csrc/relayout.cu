@@ -432,7 +432,8 @@ extern "C" int t10_relayout_blocks(int dtype, const void* d_src, void* d_dst, in
     T10_LAUNCH_CHECK();
     return T10_OK;
   }
-  static int occ[4] = {0, 0, 0, 0};
+  static int occ_by_dev[T10_MAX_DEVICES][4] = {{0}};
+  int* occ = occ_by_dev[cur_device()];
 #define T10_RL_LAUNCH(T, CHK, SLOT)                                                                   \
   do {                                                                                                \
     auto kern = k_relayout_blocks<T, CHK, false>;                                                     \
@@ -465,7 +466,8 @@ extern "C" int t10_relayout_index(int dtype, const void* d_src, void* d_dst, int
   T10_REQUIRE(((uintptr_t)d_dst & 15) == 0 && ((uintptr_t)d_index & 7) == 0, T10_ERR_INVALID,
               "relayout_index: destination must be 16-byte aligned");
   const int64_t npairs = n / 2;
-  static int occ = 0;
+  static int occ_by_dev1[T10_MAX_DEVICES] = {0};
+  int& occ = occ_by_dev1[cur_device()];
   if (occ == 0) {
     T10_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relayout_index<double>, RI_THREADS, 0));
     if (occ < 1) occ = 1;

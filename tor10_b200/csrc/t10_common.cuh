@@ -33,6 +33,15 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
 
+// ordinal of the current device, clamped into [0, T10_MAX_DEVICES): index of per-device set-up caches (function
+// attributes and occupancy are properties of a (kernel, device) pair, not of the process -- ADVICE r1)
+constexpr int T10_MAX_DEVICES = 64;
+static inline int cur_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= T10_MAX_DEVICES) d = 0;
+  return d;
+}
+
 // stream-ordered scratch that frees itself (used only while building maps)
 struct Scratch {
   cudaStream_t st;
