@@ -21,7 +21,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_SHARD_MIN_MFLOP="0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import tor10_b200 as T
@@ -65,7 +65,7 @@ def _worker_streamk(rank, world, port, q):
     enough for a test: tiles are cut across CTAs, parked partials are fixed up, the finished tiles are pushed to
     both ranks from the staging tile that aliases the pipeline stages."""
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_GGEMM_CFG="46",
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_SHARD_MIN_MFLOP="0", TOR10_GGEMM_CFG="46",
                       TOR10_GGEMM_STREAMK="force")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -113,7 +113,7 @@ def _worker_resident(rank, world, port, q):
     operand (foreign sectors pulled).  Ten rounds wrap the ring of result arenas (write-after-read protocol).
     Everything is compared with the same chain on one GPU (rounding level) and, first link, with the oracle."""
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_SHARD_MIN_MFLOP="0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import tor10_b200 as T

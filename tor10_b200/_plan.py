@@ -97,8 +97,6 @@ def clear_caches():
     if par is not None:
         par._SYMM.clear()
         par._STAGE.clear()
-        if par._RES["world"] is not None:
-            par._RES["world"].pools.clear()
 
 
 def _tensor_bytes(*ts):
@@ -860,6 +858,7 @@ class GemmGroup:
 
 _PLAN_SERIAL = itertools.count()
 _PDL = os.environ.get("TOR10_PDL", "1") == "1"
+_SHARD_MIN_FLOP = float(os.environ.get("TOR10_SHARD_MIN_MFLOP", "5")) * 1e6
 
 
 class ContractPlan:
@@ -1096,7 +1095,9 @@ def _run_resident(self, a, b):
         for o in hit[1]:
             need[o] = max(need[o], res.seq)
         rel_args[which] = hit
-    pool = rw.pool((self.serial, "out"), self.Lo.arena_elems + ARENA_ALIGN, dt, a.device)
+    pool = self._pool
+    if pool is False:          # first run: the ring of result arenas belongs to the plan (freed with it)
+        pool = self._pool = rw.new_pool(self.Lo.arena_elems + ARENA_ALIGN, dt, a.device)
     slot, war = pool.acquire() if pool is not None else (None, 0)
     need = [max(n, war) if r != rank else 0 for r, n in enumerate(need)]
     rw.wait(need)
@@ -1143,6 +1144,7 @@ def _make_out(self, Cc):
 
 ContractPlan._make_out = _make_out
 ContractPlan._out_tpl = None
+ContractPlan._pool = False
 
 
 ContractPlan._run_resident = _run_resident
@@ -1159,6 +1161,11 @@ def contract_key(a, b):
 def get_contract_plan(a, b):
     from . import parallel
     shard = parallel.current_shard()
+    if shard is not None and _SHARD_MIN_FLOP > 0:
+        # small contractions are not worth a launch per rank plus bookkeeping: below the threshold every rank
+        # computes the whole (replicated) result; the estimate is the dense-equivalent row x col x k of the operands
+        if 2.0 * a._layout.nnz * max(b._layout.nnz, 1) ** 0.5 < _SHARD_MIN_FLOP:
+            shard = None
     rk = None
     if shard and a._res is not None and parallel._STATE["transport"] in ("resident", "pull"):
         rk = a._res.key()          # ownership may propagate from a resident first operand

@@ -418,20 +418,18 @@ class ResidentWorld:
         from . import _lib
         _lib.check(_lib.load().t10_signal_flags(1, self.sig_ptrs, int(value), _lib.stream_ptr()))
 
-    def pool(self, key, n, dtype, device):
-        """The plan's ring of symmetric result arenas, or None when symmetric memory of that size cannot be had (the
-        plan's results then live in private memory: still sector-resident, completed by a collective on demand)."""
-        p = self.pools.get(key, False)
-        if p is False:
-            try:
-                p = ArenaPool(self, n, dtype, device)
-            except RuntimeError:
-                p = None
-            ok = torch.tensor([1 if p is not None else 0], device=device, dtype=torch.int32)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)        # every rank takes the same decision
-            if int(ok.item()) == 0:
-                p = None
-            self.pools[key] = p
+    def new_pool(self, n, dtype, device):
+        """A ring of symmetric result arenas for one plan (owned by the plan: evicting the plan frees it), or None
+        when symmetric memory of that size cannot be had (the plan's results then live in private memory: still
+        sector-resident, completed by a collective on demand)."""
+        try:
+            p = ArenaPool(self, n, dtype, device)
+        except RuntimeError:
+            p = None
+        ok = torch.tensor([1 if p is not None else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)            # every rank takes the same decision
+        if int(ok.item()) == 0:
+            p = None
         return p
 
 
