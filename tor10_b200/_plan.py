@@ -545,6 +545,11 @@ def pick_tile_cfg(problems, sharded=False, base_aligned=False):
     return 40
 
 
+def _sm_count_of(device):
+    with torch.cuda.device(device):
+        return _sm_count()
+
+
 def _sm_count():
     nsm, z = C.c_int(0), C.c_int(0)
     check(_lib.load().t10_device_props(torch.cuda.current_device(), C.byref(nsm), C.byref(z), C.byref(z), C.byref(z)))
@@ -617,7 +622,10 @@ class GemmGroup:
         self.tma = False
         self._tma_maps = {}
         if (dtype == torch.float64 and self.tile_cfg in (46, 40) and self.ntiles > 0 and self.aligned
-                and not sharded and os.environ.get("TOR10_GGEMM_TMA", "1") == "1"):
+                and not sharded and os.environ.get("TOR10_GGEMM_TMA", "1") == "1"
+                # a lone small GEMM (the chi = 32 products of iTEBD) gains nothing from the TMA feed and would pay
+                # for a tensor-map encode + upload whenever its operands move: the cp.async kernel takes those
+                and (self.nprob > 1 or self.ntiles >= 2 * _sm_count_of(device))):
             # TMA-fed kernel (ggemm_tma.cu): stream-K pieces when there is enough work to cut, whole tiles in LPT
             # slots otherwise -- one kernel, one table format
             nres = C.c_int(0)
