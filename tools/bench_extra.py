@@ -266,7 +266,7 @@ def c5_peps(D=8, chi=512):
                  for pl in plans)
     emit(item="C5 PEPS double-layer site absorption D=%d chi=%d" % (D, chi), ms=ms, gflop=flops / 1e9,
          gflops=flops / ms / 1e6, algorithmic_GB=nbytes / 1e9, GBs=nbytes / ms / 1e6,
-         arithmetic_intensity=flops / nbytes, relayouts=sum((pl.rel_a is not None) + (pl.rel_b is not None) for pl in plans),
+         arithmetic_intensity=(flops / nbytes if nbytes else None), relayouts=sum((pl.rel_a is not None) + (pl.rel_b is not None) for pl in plans),
          index_replay=[("segments" if r.d_seg is not None else "runs" if r.d_runs is not None else "index" if r.d_index is not None else "blocks") for pl in plans for r in (pl.rel_a, pl.rel_b) if r is not None],
          note="Network.Launch of 3 U1 tensors (2 Contracts + final Permute), plans replayed; contracting over single "
               "D=8 bonds makes this HBM-bound (K <= 64 per sector)")

@@ -267,7 +267,13 @@ def _sector_svds(one, views, mine, device):
     Sectors too large for the one-CTA kernel are therefore factorised CONCURRENTLY, one host thread + CUDA stream per
     worker (torch releases the GIL inside the call; cuSOLVER handles are per thread and stream), largest first; the
     streams are joined back into the current stream before anything is returned (no hidden streams)."""
-    nwork = int(os.environ.get("TOR10_SVD_STREAMS", "16"))
+    nwork = os.environ.get("TOR10_SVD_STREAMS")
+    if nwork is None:
+        # one host thread per concurrent SVD: share the box's cores between the ranks running on it (2 ranks x 16
+        # threads on 16 cores measured 0.22 s against 0.096 s for one rank)
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+        nwork = max(2, min(16, (os.cpu_count() or 16) // max(local, 1)))
+    nwork = int(nwork)
     fac = {}
     rest = []
     for i in mine:
