@@ -1,13 +1,13 @@
 import ctypes as C, torch, json, sys, os
-lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libsvddbg.so"))
+lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", sys.argv[1] if len(sys.argv) > 1 else "libsvddbg.so"))
 dev = torch.device("cuda", 0)
 for n in (64, 32, 16):
     x = torch.rand((n, n), device=dev, dtype=torch.float64)
     u = torch.empty((n, n), device=dev, dtype=torch.float64); s = torch.empty(n, device=dev, dtype=torch.float64); vh = torch.empty((n, n), device=dev, dtype=torch.float64)
     info = torch.zeros(8, device=dev, dtype=torch.int32)
-    prob = (C.c_int64 * 8)(n, n, 0, n, 1, 0, 0, 0)
+    prob = (C.c_int64 * 9)(n, n, 0, n, 1, 0, 0, 0, -1)
     for _ in range(3):
-        rc = lib.t10_svd_small(0, C.c_int64(1), prob, C.c_void_p(x.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(s.data_ptr()), C.c_void_p(vh.data_ptr()), C.c_void_p(info.data_ptr()), None)
+        rc = lib.t10_svd_small(0, C.c_int64(1), prob, C.c_void_p(x.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(s.data_ptr()), C.c_void_p(vh.data_ptr()), None, C.c_void_p(info.data_ptr()), None)
     torch.cuda.synchronize()
     v = info.cpu().tolist()
     sweeps = v[0] >> 1

@@ -34,7 +34,8 @@ struct SvdBatch {                     // no copy -- the launch can be captured i
   SvdProb p[SV_BATCH];
 };
 
-constexpr int SV_LPP = 8;             // lanes per column pair: four pairs share a warp (the rotation angle is a long
+constexpr int SV_LPP = 16;            // lanes per column pair: two pairs share a warp (measured at n = 64: 5490 cycles per
+                                      // round with 4 lanes, 3400 with 8, 2690 with 16, 3610 with 32; the rotation angle is a long
                                       // scalar dependency chain; one warp per pair is issue-bound on it at n = 64)
 
 template <typename T>
