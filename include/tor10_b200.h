@@ -163,7 +163,7 @@ int t10_relayout_segments(int dtype, int nsrc, const void* const* h_src, void* d
                           const int32_t* d_seg, t10_stream_t stream);
 
 /* Multi-GPU sector gather over NVLink peer memory (no reference counterpart: the reference has no
- * multi-device code).  dst[lo_i .. hi_i) = src_i[lo_i .. hi_i) for nseg <= 16 slices, where src_i are
+ * multi-device code).  dst[lo_i .. hi_i) = src_i[lo_i .. hi_i) for nseg <= 64 slices, where src_i are
  * peer-mapped (symmetric-memory) staging buffers of the other ranks; bounds multiples of 16 bytes.
  * One launch pulls from all peers at once.                                                 */
 int t10_gather_peers(int dtype, void* d_dst, int nseg, const void* const* h_src, const int64_t* h_lo,

@@ -561,12 +561,13 @@ extern "C" int t10_relayout_segments(int dtype, int nsrc, const void* const* h_s
 // Sector gather over NVLink peer memory (multi-GPU Contract): every rank's finished sectors sit in its
 // own symmetric staging buffer; this kernel PULLS all the slices this rank does not own (P2P loads,
 // 16-byte vectors, all peers in flight at once) into the local output arena.  One launch, no NCCL.
+constexpr int PEER_MAXSEG = 64;
 struct PeerSegs {
   int n;
-  const void* src[16];   // peer (or local) staging base pointers
-  int64_t lo[16];        // element range [lo, hi) of the slice, same offsets in staging and arena
-  int64_t hi[16];
-  int64_t vec_start[17]; // prefix sum of slice lengths in 16-byte vectors
+  const void* src[PEER_MAXSEG];   // peer (or local) staging base pointers
+  int64_t lo[PEER_MAXSEG];        // element range [lo, hi) of the slice, same offsets in staging and arena
+  int64_t hi[PEER_MAXSEG];
+  int64_t vec_start[PEER_MAXSEG + 1]; // prefix sum of slice lengths in 16-byte vectors
 };
 
 template <typename T>
@@ -575,9 +576,12 @@ k_gather_peers(T* __restrict__ dst, const __grid_constant__ PeerSegs ps) {
   constexpr int VE = 16 / sizeof(T);
   const int64_t total = ps.vec_start[ps.n];
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-    int sgm = 0;
+    int sgm = 0, hi_ = ps.n - 1;          // (bisection: up to 64 slices)
 #pragma unroll 1
-    while (v >= ps.vec_start[sgm + 1]) ++sgm;
+    while (sgm < hi_) {
+      const int mid = (sgm + hi_) >> 1;
+      if (v >= ps.vec_start[mid + 1]) sgm = mid + 1; else hi_ = mid;
+    }
     const int64_t e = ps.lo[sgm] + (v - ps.vec_start[sgm]) * VE;
     const int4 val = *reinterpret_cast<const int4*>(reinterpret_cast<const T*>(ps.src[sgm]) + e);
     *reinterpret_cast<int4*>(dst + e) = val;
@@ -632,7 +636,7 @@ extern "C" int t10_wait_copy(int dtype, void* d_dst, const void* d_src, int64_t 
 extern "C" int t10_gather_peers(int dtype, void* d_dst, int nseg, const void* const* h_src,
                                 const int64_t* h_lo, const int64_t* h_hi, t10_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  T10_REQUIRE(nseg >= 0 && nseg <= 16, T10_ERR_INVALID, "gather_peers: at most 16 segments");
+  T10_REQUIRE(nseg >= 0 && nseg <= PEER_MAXSEG, T10_ERR_INVALID, "gather_peers: at most %d segments", PEER_MAXSEG);
   T10_REQUIRE(dtype == T10_F64 || dtype == T10_F32, T10_ERR_UNSUPPORTED, "gather_peers: dtype %d", dtype);
   const int ve = dtype == T10_F64 ? 2 : 4;
   PeerSegs ps;

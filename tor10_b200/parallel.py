@@ -473,6 +473,9 @@ def fetch_plan(layout, res, needed):
     return out
 
 
+_PULL_ARGS = {}
+
+
 def pull_sectors(t, needed):
     """Make the `needed` sectors of resident tensor t valid in this rank's arena: one pull kernel over the owners'
     NVLink peer mappings (after acquiring their progress).  No-op for sectors already here."""
@@ -489,14 +492,32 @@ def pull_sectors(t, needed):
     for o in plan:
         need[o] = res.seq
     rw.wait(need)
-    segs = [(res.slot.peer_ptr(o), lo, hi) for o, rs in sorted(plan.items()) for lo, hi in rs]
+    # one launch for (up to 64) slices: neighbouring sectors of one owner travel as one slice; the argument arrays are
+    # cached per slot and request (a "pull" transport asks for the same sectors every step)
+    key = (id(res.slot), tuple(needed) if not isinstance(needed, range) else (needed.start, needed.stop),
+           res.owner.tobytes())
+    args = _PULL_ARGS.get(key)
+    if args is None:
+        segs = []
+        for o, rs in sorted(plan.items(), key=lambda kv: (kv[0] - res.rank) % res.world):   # start with the next rank
+            for lo, hi in sorted(rs):
+                if segs and segs[-1][0] == o and segs[-1][2] >= lo:
+                    segs[-1][2] = max(segs[-1][2], hi)
+                else:
+                    segs.append([o, lo, hi])
+        args = []
+        for i in range(0, len(segs), 64):
+            part = segs[i:i + 64]
+            n = len(part)
+            args.append((n, (C.c_void_p * n)(*[res.slot.peer_ptr(o) for o, _, _ in part]),
+                         (C.c_int64 * n)(*[a for _, a, _ in part]), (C.c_int64 * n)(*[b for _, _, b in part])))
+        if len(_PULL_ARGS) > 256:
+            _PULL_ARGS.clear()
+        _PULL_ARGS[key] = args
     arena = t._arena
-    for i in range(0, len(segs), 16):
-        part = segs[i:i + 16]
-        n = len(part)
-        _lib.check(_lib.load().t10_gather_peers(
-            _lib.dtype_code(arena.dtype), arena.data_ptr(), n, (C.c_void_p * n)(*[p for p, _, _ in part]),
-            (C.c_int64 * n)(*[a for _, a, _ in part]), (C.c_int64 * n)(*[b for _, _, b in part]), _lib.stream_ptr()))
+    for n, ptrs, los, his in args:
+        _lib.check(_lib.load().t10_gather_peers(_lib.dtype_code(arena.dtype), arena.data_ptr(), n, ptrs, los, his,
+                                                _lib.stream_ptr()))
     for s in needed:
         res.valid[s] = True
     # the peers read THIS rank's slot the same way: they are done once they have published their next operation
