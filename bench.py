@@ -320,7 +320,7 @@ def main():
     # ---- the same step through the other transports: "pull" / "fused" gather the result on every rank --------
     others = {}
     if world > 1:
-        for tr in ("resident", "pull", "fused"):
+        for tr in ("resident", "push", "pull", "fused"):
             if tr == plan._transport:
                 continue
             try:
@@ -562,6 +562,8 @@ def main():
                                     "on the tensor, later contractions read them in place or fetch foreign sectors over "
                                     "NVLink peer memory, gathered on demand); no collective on the data path",
                         "pull": "resident, then every rank pulls the other ranks' sectors over NVLink peer memory",
+                        "push": "all-gather fused into the TMA-fed GEMM: finished tiles stored from the accumulator "
+                                "registers into every rank's ring slot over NVLink, progress words, no staging copy",
                         "fused": "all-gather fused into the GEMM epilogue (tiles stored into all ranks' symmetric "
                                  "staging arenas over NVLink, system-scope flags, one wait+copy kernel)",
                         "p2p": "symmetric-memory staging + device barrier + one pull kernel",
@@ -580,7 +582,7 @@ def main():
                             "downloads its own output sectors" if world > 1 else "Whole operands in, whole result out"))},
         "fp32_contract": fp32_info,
         "gpu_launches": int(args.steps * ((1 if plan.rel_a is not None else 0) + (1 if plan.rel_b is not None else 0)
-                                          + 1 + ((1 if plan._transport in ("fused", "p2p", "pull") else 0) if world > 1 else 0))),
+                                          + 1 + ((1 if plan._transport in ("fused", "p2p", "pull", "push") else 0) if world > 1 else 0))),
         "roofline": {"kernel": ("k_ggemm_f64_tma (grouped DMMA GEMM, TMA producer warp + mbarrier ring, mixed tile "
                                 "shapes, stream-K)" if getattr(plan.gemm, "tma", False) else
                                 "k_ggemm_f64_mixed_sk (grouped DMMA GEMM, mixed tile shapes, stream-K)"

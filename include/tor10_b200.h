@@ -265,7 +265,14 @@ int t10_ggemm_tma_encode(int64_t nprob, const t10_gemm_problem* h_prob, const vo
 int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const t10_gemm_problem* d_prob, int64_t npieces,
                   const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots, const int32_t* d_slot_start,
                   void* d_ws, int32_t* d_flags, int32_t epoch, int pdl,
-                  int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr, t10_stream_t stream);
+                  int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr,
+                  int npush, void* const* h_push, t10_stream_t stream);
+
+/* t10_ggemm_tma with npush > 0 (fused GEMM -> all-gather, "push" transport): every finished tile is also stored,
+ * straight from the accumulator registers, into h_push[0..npush) -- the result arenas of the OTHER ranks through
+ * their NVLink peer mappings, at the same element offsets as in d_C -- so the transfer rides under the remaining
+ * pieces' math; the completion signal (nsig > 0 required) then covers the remote stores, and a rank that has
+ * acquired every peer's progress word (t10_wait_flags) holds the whole result.                              */
 
 /* Progress words of sector-resident multi-GPU runs (no reference counterpart: the reference is single-device).
  * Every rank keeps ONE uint64 progress word in symmetric memory: the number of resident operations it has

@@ -178,7 +178,7 @@ class Emu:
     def t10_ggemm_tma_encode(self, nprob, prob, A, B, hmaps):
         arr(hmaps, 2, np.int64)[:] = [A or 0, B or 0]       # the emulated "maps" are just the operand bases
         return 0
-    def t10_ggemm_tma(self, maps, Cc, nprob, prob, npieces, tiles, pieces, nslots, slots, ws, flags, epoch, pdl, nsig, sigp, sigv, done, st):
+    def t10_ggemm_tma(self, maps, Cc, nprob, prob, npieces, tiles, pieces, nslots, slots, ws, flags, epoch, pdl, nsig, sigp, sigv, done, npush, push, st):
         A, B = (int(x) for x in arr(maps, 2, np.int64))
         return self.t10_ggemm(0, 46, A, B, Cc, nprob, prob, npieces, tiles, nslots, slots, None, st)
     def t10_ggemm_slots(self, dt, cfg, out):

@@ -176,7 +176,7 @@ def _worker_resident(rank, world, port, q):
         return net.Launch().Contiguous()
 
     net_ref = [x.clone() for x in launch().Storage]
-    for tr in ("resident", "pull"):
+    for tr in ("resident", "pull", "push"):
         parallel.enable(transport=tr)
         for it in range(10):
             c, d, f, g = chain()

@@ -19,7 +19,7 @@ A, B = bench.c3a_specs(int(os.environ.get("CHI", "4096")))
 a = psym(T, A, seed=1003, device=dev); b = psym(T, B, seed=1004, device=dev)
 single = [x.clone() for x in T.Contract(a, b).Storage]
 out = {}
-for tr in os.environ.get("TRANSPORTS", "resident,pull,fused,nccl").split(","):
+for tr in os.environ.get("TRANSPORTS", "resident,push,pull,fused,nccl").split(","):
     parallel.enable(transport=tr)
     _plan.clear_caches()
     first, repro, err = None, True, 0.0

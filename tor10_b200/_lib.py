@@ -79,7 +79,7 @@ SIGNATURES = {
     "t10_svd_small": [_i, _l, _p, _p, _p, _p, _p, _p, _p, _p],
     "t10_ggemm_tma_slots": [_p],
     "t10_ggemm_tma_encode": [_l, _p, _p, _p, _p],
-    "t10_ggemm_tma": [_p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _i, _i, _p, C.c_uint64, _p, _p],
+    "t10_ggemm_tma": [_p, _p, _l, _p, _l, _p, _p, _l, _p, _p, _p, _i, _i, _i, _p, C.c_uint64, _p, _i, _p, _p],
     "t10_signal_flags": [_i, _p, C.c_uint64, _p],
     "t10_wait_flags": [_i, _p, _p, _l, _p, _p],
     "t10_relayout_runs": [_i, _p, _p, _l, _p, _l, _p, _p],

@@ -564,7 +564,8 @@ FALLBACK_CFG = 3
 class GemmGroup:
     """Problem table + tile table on the device."""
 
-    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True, sharded=False, resident=False):
+    def __init__(self, problems, device, dtype, tile_cfg=None, base_aligned=True, sharded=False, resident=False,
+                 force_tma=False):
         lib = _lib.load()
         if resident:
             sharded = False       # a rank's share of a resident contraction is an ordinary group: no fused push
@@ -625,7 +626,8 @@ class GemmGroup:
                 and not sharded and os.environ.get("TOR10_GGEMM_TMA", "1") == "1"
                 # a lone small GEMM (the chi = 32 products of iTEBD) gains nothing from the TMA feed and would pay
                 # for a tensor-map encode + upload whenever its operands move: the cp.async kernel takes those
-                and (self.nprob > 1 or self.ntiles >= 2 * _sm_count_of(device))):
+                # (force_tma: the "push" transport needs the same kernel on every rank, whatever its share)
+                and (force_tma or self.nprob > 1 or self.ntiles >= 2 * _sm_count_of(device))):
             # TMA-fed kernel (ggemm_tma.cu): stream-K pieces when there is enough work to cut, whole tiles in LPT
             # slots otherwise -- one kernel, one table format
             nres = C.c_int(0)
@@ -818,10 +820,12 @@ class GemmGroup:
         self.sk_epoch = self.sk_epoch % 2000000000 + 1
         nsig, sig_ptrs, sig_val, done = (0, None, 0, None) if signal is None else \
             (len(signal[0]), signal[0], int(signal[1]), signal[2].data_ptr())
+        push = signal[3] if (signal is not None and len(signal) > 3) else None
         check(lib.t10_ggemm_tma(d_maps.data_ptr(), Cc.data_ptr(), self.nprob, self.d_prob.data_ptr(), self.sk_npieces,
                                 self.d_sk_tiles.data_ptr(), self.d_sk_pieces.data_ptr(), self.sk_nslots,
                                 self.d_sk_slots.data_ptr(), self.d_sk_ws.data_ptr(), self.d_sk_flags.data_ptr(),
-                                self.sk_epoch, 1 if pdl else 0, nsig, sig_ptrs, sig_val, done, _lib.stream_ptr()))
+                                self.sk_epoch, 1 if pdl else 0, nsig, sig_ptrs, sig_val, done,
+                                len(push) if push is not None else 0, push, _lib.stream_ptr()))
 
     def fusable(self):
         """The fused GEMM -> all-gather epilogue exists in the fp64 kernels 0..3 (t10_ggemm_allgather)."""
@@ -952,14 +956,14 @@ class ContractPlan:
             self.ranges = arena_ranges(Lo, bounds)
             owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(Lo.nsec), side="right")
             self.inherited = False
-            if self._transport in ("resident", "pull") and a._res is not None and ident_a \
+            if self._transport in ("resident", "pull", "push") and a._res is not None and ident_a \
                     and a._res.world == world:
                 # ownership propagates: output sector q lives where A's row sector q lives, so a chain
                 # of contractions reads its running operand in place on every rank
                 from .parallel import inherit_owner
                 owner = inherit_owner(a._res.owner, matched, Lo.nsec, cost, world)
                 self.inherited = True
-            elif self._transport in ("none", "resident", "pull") or (self._transport == "fused" and a.dtype == torch.float64
+            elif self._transport in ("none", "resident", "pull", "push") or (self._transport == "fused" and a.dtype == torch.float64
                                              and pick_tile_cfg(None) in FUSABLE_CFGS):
                 # the fused GEMM -> all-gather stores tiles, not arena slices (and sharded results are not gathered
                 # at all): ownership need not be contiguous, so the sectors are balanced by LPT (the contiguous
@@ -982,8 +986,12 @@ class ContractPlan:
         for i, (ob, ab, bb) in enumerate(matched):
             prob[i] = (pa.off[ab], pb.off[bb], Lo.arena_off[ob], La.rows[ab], Lb.cols[bb], La.cols[ab],
                        pa.ld[ab], pb.ld[bb], Lo.ld[ob])
-        self.gemm = GemmGroup(prob, dev, a.dtype, sharded=shard is not None and shard[1] > 1,
-                              resident=self._transport in ("resident", "pull", "none"))
+        self.gemm = GemmGroup(prob, dev, a.dtype,
+                              # "push": the same kernel on every rank whatever its share (the ranks must agree on who pushes)
+                              tile_cfg=46 if (self._transport == "push" and a.dtype == torch.float64) else None,
+                              sharded=shard is not None and shard[1] > 1,
+                              resident=self._transport in ("resident", "pull", "push", "none"),
+                              force_tma=self._transport == "push")
         self._res_segs = {}
         self.flops = self.gemm.flops
         self.gemm_bytes = self.gemm.bytes
@@ -994,11 +1002,11 @@ class ContractPlan:
         if b.dtype != dt:
             raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (dt, b.dtype))
         with _lib.on_device(a.device):
-            res_ok = self.shard is not None and self.shard[1] > 1 and self._transport in ("resident", "pull")
+            res_ok = self.shard is not None and self.shard[1] > 1 and self._transport in ("resident", "pull", "push")
             A = a._arena_tensor(resident_ok=res_ok)
             B = b._arena_tensor(resident_ok=res_ok)
             sharded = self.shard is not None and self.shard[1] > 1
-            if sharded and self._transport in ("resident", "pull"):
+            if sharded and self._transport in ("resident", "pull", "push"):
                 return self._run_resident(a, b)
             fused = sharded and self._transport == "fused" and self.gemm.fusable()
             need_zero = (not self.all_matched) or (self.shard is not None and self._transport == "none")
@@ -1121,18 +1129,35 @@ def _run_resident(self, a, b):
             ptrs = [src.data_ptr()] + [t._res.slot.peer_ptr(o) for o in hit[1]]
             rel.run_segments(ptrs, dst, _lib.dtype_code(dt), seg=hit[0], nseg=int(hit[0].shape[0]))
     Cc = slot.tensor() if slot is not None else self.Lo.new_arena(dt, zero=not self.all_matched)
+    # (decided identically on every rank: fp64 symmetric sectors are always aligned, so a rank with work runs the TMA
+    # kernel; a rank without any only signals)
+    pushing = self._transport == "push" and slot is not None and dt == torch.float64 \
+        and (getattr(self.gemm, "tma", False) or self.gemm.nprob == 0)
+    sig = (rw.sig_ptrs, seq, rw.done_ctr)
+    if pushing:
+        # fused GEMM -> all-gather: finished tiles are stored into every other rank's ring slot as well
+        import ctypes as C
+        ptrs = slot.pool.push_args.get(slot.index)
+        if ptrs is None:
+            ptrs = slot.pool.push_args[slot.index] = (C.c_void_p * (world - 1))(
+                *[slot.peer_ptr(r) for r in range(world) if r != rank])
+        sig = sig + (ptrs,)
     self.gemm.run(Ap if Ap is not None else A, Bp if Bp is not None else B, Cc,
-                  pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL,
-                  signal=(rw.sig_ptrs, seq, rw.done_ctr))
+                  pdl=(self.rel_a is not None or self.rel_b is not None) and _PDL, signal=sig)
     out = self._make_out(Cc)
     out._res = parallel.Residency(world, rank, self.sector_owner, seq, slot, self._own_valid)
     if slot is not None:
         slot.holder = weakref.ref(out)
-    if self._transport == "pull":
+    if self._transport == "pull" or (self._transport == "push" and not pushing):
         if slot is not None:
             parallel.pull_sectors(out, range(self.Lo.nsec))
         else:
             parallel.gather_collective(out)
+    elif pushing:
+        # the whole result is here once every peer has published this operation (its pushes precede its signal)
+        rw.wait([seq if r != rank else 0 for r in range(world)])
+        out._res.valid[:] = True
+        slot.last_read = max(slot.last_read, seq)
     return out
 
 
@@ -1175,7 +1200,7 @@ def get_contract_plan(a, b):
         if 2.0 * a._layout.nnz * max(b._layout.nnz, 1) ** 0.5 < _SHARD_MIN_FLOP:
             shard = None
     rk = None
-    if shard and a._res is not None and parallel._STATE["transport"] in ("resident", "pull"):
+    if shard and a._res is not None and parallel._STATE["transport"] in ("resident", "pull", "push"):
         rk = a._res.key()          # ownership may propagate from a resident first operand
     key = (contract_key(a, b), shard, parallel._STATE["transport"] if shard else None, rk)
     pl = _CONTRACTS.get(key)

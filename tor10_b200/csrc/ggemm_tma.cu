@@ -90,6 +90,12 @@ struct TgSignal {
   unsigned long long* flag[8];
   unsigned long long value;
   int* done_ctr;                   // zero-initialised arrival counter of this launch (reset on exit)
+  // Fused GEMM -> all-gather ("push" transport): every finished tile is ALSO stored, straight from the accumulator
+  // registers, into the result arenas of the other ranks (npush NVLink peer mappings, same element offsets), so the
+  // transfer rides under the remaining pieces' math; the completion signal then covers the remote stores too
+  // (system-scope fences), and a rank that has acquired every peer's progress word holds the whole result.
+  int npush;
+  double* push[7];
 };
 
 template <int TG_STAGES, int MIN_CTAS>
@@ -307,10 +313,38 @@ k_ggemm_f64_tma(const CUtensorMap* __restrict__ maps, double* __restrict__ Cbase
         }
       }
     }
+    if (sig.npush > 0) {
+      const int64_t base = p.c_off;
+#pragma unroll 1
+      for (int q = 0; q < sig.npush; ++q) {
+        double* Cq = sig.push[q] + base;
+        const bool q16 = ((p.ldc & 1) == 0) && ((p.c_off & 1) == 0) && (((uintptr_t)sig.push[q] & 15) == 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = m0 + wm0 + i * 8 + g;
+          if (r >= m_end) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = n0 + wn0 + j * 8 + 2 * tig;
+            double* o = Cq + (int64_t)r * p.ldc + c;
+            if (c + 1 < n_end) {
+              if (q16) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
+              else { o[0] = acc[i][j][0]; o[1] = acc[i][j][1]; }
+            } else if (c < n_end) {
+              o[0] = acc[i][j][0];
+            }
+          }
+        }
+      }
+    }
   }
   if (sig.n > 0) {
+    // remote tile stores: EVERY storing thread orders its own at system scope (a fence by thread 0 alone behind the
+    // CTA barrier let a consumer on the peer see the progress word before the tiles: measured, 2-GPU chain test)
+    if (sig.npush > 0) __threadfence_system();
     tg_consumer_sync();              // every DMMA warp's tile stores precede thread 0's fence
     if (threadIdx.x == 0) {
+      if (sig.npush > 0) __threadfence_system();
       __threadfence();               // release this CTA's tile stores before the arrival ...
       if (atomicAdd(sig.done_ctr, 1) == (int)gridDim.x - 1) {
         *sig.done_ctr = 0;
@@ -445,8 +479,13 @@ extern "C" int t10_ggemm_tma_encode(int64_t nprob, const t10_gemm_problem* h_pro
   return T10_OK;
 }
 
-static int tg_fill_signal(TgSignal* sig, int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr) {
+static int tg_fill_signal(TgSignal* sig, int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr,
+                          int npush = 0, void* const* h_push = nullptr) {
   memset(sig, 0, sizeof(*sig));
+  T10_REQUIRE(npush >= 0 && npush <= 7 && (npush == 0 || (h_push && nsig > 0)), T10_ERR_INVALID,
+              "push: at most 7 peer arenas, and a completion signal");
+  sig->npush = npush;
+  for (int i = 0; i < npush; ++i) sig->push[i] = (double*)h_push[i];
   T10_REQUIRE(nsig >= 0 && nsig <= 8, T10_ERR_INVALID, "signal: at most 8 ranks");
   T10_REQUIRE(nsig == 0 || (h_sig_flags && d_done_ctr), T10_ERR_INVALID, "signal: flags need an arrival counter");
   sig->n = nsig;
@@ -489,10 +528,10 @@ extern "C" int t10_ggemm_tma(const void* d_maps, void* d_C, int64_t nprob, const
                              int64_t npieces, const int32_t* d_tiles, const int32_t* d_pieces, int64_t nslots,
                              const int32_t* d_slot_start, void* d_ws, int32_t* d_flags, int32_t epoch, int pdl,
                              int nsig, void* const* h_sig_flags, uint64_t sig_value, int32_t* d_done_ctr,
-                             t10_stream_t stream) {
+                             int npush, void* const* h_push, t10_stream_t stream) {
   TgSignal sig;
   {
-    int rc = tg_fill_signal(&sig, nsig, h_sig_flags, sig_value, d_done_ctr);
+    int rc = tg_fill_signal(&sig, nsig, h_sig_flags, sig_value, d_done_ctr, npush, h_push);
     if (rc != T10_OK) return rc;
   }
   if (npieces == 0 || nprob == 0) {      // a rank without work still has to signal

@@ -30,11 +30,15 @@ def enable(group=None, transport="auto"):
                            on demand (see the second half of this module),
                   "pull"  = resident, then every rank pulls the other ranks' sectors at once (gathered result,
                            no staging copy),
+                  "push"  = fused GEMM -> all-gather on the TMA kernel: finished tiles are stored from the
+                           accumulator registers into every rank's ring slot over NVLink while the remaining pieces
+                           compute; a rank holds the whole result once it has acquired every peer's progress word
+                           (gathered result, no staging, no copy),
                   "auto"  = fused on NCCL process groups when symmetric memory is available, else nccl."""
     if not dist.is_initialized():
         raise RuntimeError("tor10_b200.parallel.enable(): torch.distributed is not initialised")
-    if transport not in ("auto", "fused", "p2p", "nccl", "none", "resident", "pull"):
-        raise ValueError("transport must be auto | fused | p2p | nccl | none | resident | pull")
+    if transport not in ("auto", "fused", "p2p", "nccl", "none", "resident", "pull", "push"):
+        raise ValueError("transport must be auto | fused | p2p | nccl | none | resident | pull | push")
     _STATE["group"] = group
     _STATE["enabled"] = True
     _STATE["transport"] = transport
@@ -347,6 +351,7 @@ class ArenaPool:
         base = [int(hdl.get_buffer(r, (depth * self.stride,), dtype).data_ptr()) for r in range(rw.world)]
         self.peer_ptrs = [[base[r] + k * self.stride * esz for r in range(rw.world)] for k in range(depth)]
         self.slots = [_Slot(self, k) for k in range(depth)]
+        self.push_args = {}
         self.turn = 0
         dist.barrier(group=rw.group)
 
