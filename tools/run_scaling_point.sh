@@ -1,4 +1,6 @@
 #!/bin/bash
+# One point of the scaling record on an N-GPU box: bench.py under torchrun (all transports, parity) + C4 / C5.
+#   gpurun --gpus N -- bash tools/run_scaling_point.sh N
 N=$1
 mkdir -p gpurun_out/r02
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2960$N bench.py --gpus $N --steps 100 --warmup 5 2> gpurun_out/r02/bench_n${N}_final.err | grep '^{' > gpurun_out/r02/bench_n${N}_final.json; echo "bench N=$N rc=$?"
