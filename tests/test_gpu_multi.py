@@ -21,7 +21,8 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_SHARD_MIN_MFLOP="0")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TOR10_SHARD_MIN_MFLOP="0",
+                      TOR10_DENSE_SHARD_MIN_GFLOP="0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import tor10_b200 as T
@@ -55,6 +56,27 @@ def _worker(rank, world, port, q):
         same = same and all(torch.equal(x, y) for x, y in zip(single32.Storage, sh32.Storage))
         parallel.disable()
         T._plan.clear_caches()
+    # untagged dense tensors: the GEMM is partitioned by output row tiles over the ranks, one NCCL all-gather
+    # assembles the result on every rank (config 2 shape at chi = 256)
+    chi, d = 256, 2
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((chi, d, d, chi), generator=g, dtype=torch.float64).to("cuda:%d" % rank)
+    y = torch.rand((d, chi, d, chi), generator=g, dtype=torch.float64).to("cuda:%d" % rank)
+    t1 = T.UniTensor(bonds=[T.Bond(chi), T.Bond(d), T.Bond(d), T.Bond(chi)], labels=[0, 2, 1, 3], rowrank=2,
+                     device=torch.device("cuda:%d" % rank))
+    t2 = T.UniTensor(bonds=[T.Bond(d), T.Bond(chi), T.Bond(d), T.Bond(chi)], labels=[2, 3, 4, 5], rowrank=2,
+                     device=torch.device("cuda:%d" % rank))
+    t1.Storage, t2.Storage = x, y
+    want = torch.tensordot(x, y, dims=([1, 3], [0, 1]))
+    one = T.Contract(t1, t2).Storage.clone()
+    parallel.enable()
+    import sys as _sys
+    if _sys.modules["tor10_b200.UniTensor"]._dense_shard(chi * d, chi * d, chi * d, x) is None:
+        same = False
+    two = T.Contract(t1, t2).Storage
+    parallel.disable()
+    err = max(err, float((two.reshape(want.shape) - want).abs().max() / want.abs().max()))
+    same = same and float((two - one).abs().max()) <= 1e-13 * float(one.abs().max())
     torch.cuda.synchronize()
     q.put((rank, "" if same else "transports disagree, or sharded result differs from the single-GPU result", err))
     dist.destroy_process_group()

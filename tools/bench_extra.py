@@ -273,7 +273,7 @@ def c5_peps(D=8, chi=512):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or (["c4", "c5"] if WORLD > 1 else ["f1", "c3", "c2", "c4", "c5", "c1"])
+    which = sys.argv[1:] or (["c4", "c5", "c2"] if WORLD > 1 else ["f1", "c3", "c2", "c4", "c5", "c1"])
     if "c4" in which:
         c4_u1z2()
     if "c5" in which:

@@ -1157,6 +1157,51 @@ def Load(filename):
 _GEMM_GROUPS = {}
 
 
+_DENSE_SHARD_MIN_FLOP = float(os.environ.get("TOR10_DENSE_SHARD_MIN_GFLOP", "2")) * 1e9
+
+
+def _dense_shard(M, N, K, A2):
+    """(rank, world) when the dense GEMM [M,K] x [K,N] is worth splitting over the ranks (untagged dense
+    tensors are partitioned by OUTPUT ROW TILES, B replicated), else None."""
+    from . import parallel
+    sh = parallel.current_shard()
+    if sh is None or A2.dtype != torch.float64 or 2.0 * M * N * K < _DENSE_SHARD_MIN_FLOP or M < 64 * sh[1]:
+        return None
+    return sh
+
+
+def _dense_gemm_sharded(A2, B2, shard):
+    """Output-row-tile partition of a dense GEMM over the ranks of one box (SURVEY 8e / BASELINE north star): every
+    rank multiplies its slab of rows of A (a multiple of 64, so slabs are whole tiles) by the replicated B, and ONE
+    NCCL all-gather over NVLink assembles the result on every rank -- the reference's single GEMM inside
+    torch.tensordot (UniTensor.py:3769) has no multi-device counterpart.  Every rank ends with the whole result (equal
+    to the one-GPU result to rounding: a slab's stream-K cuts differ from the whole problem's)."""
+    import torch.distributed as dist
+    from . import parallel
+    rank, world = shard
+    M, K = A2.shape
+    N = B2.shape[1]
+    rows = (-(-M // world) + 63) // 64 * 64                 # rows per rank: whole 64-row tiles
+    full = torch.empty((world * rows, N), device=A2.device, dtype=A2.dtype)
+    lo, hi = min(M, rank * rows), min(M, (rank + 1) * rows)
+    mine = full[rank * rows:(rank + 1) * rows]
+    if hi > lo:
+        mine[:hi - lo].copy_(_dense_gemm_local(A2[lo:hi], B2))
+    dist.all_gather_into_tensor(full, mine, group=parallel._STATE["group"])
+    return full[:M]
+
+
+def _dense_gemm_local(A2, B2):
+    """_dense_gemm without the multi-GPU split (a rank's slab)."""
+    from . import parallel
+    was = parallel._STATE["enabled"]
+    parallel._STATE["enabled"] = False
+    try:
+        return _dense_gemm(A2, B2)
+    finally:
+        parallel._STATE["enabled"] = was
+
+
 def _dense_gemm(A2, B2):
     """[M,K] x [K,N] on the family-3 kernel (single-problem group, cached per shape)."""
     M, K = A2.shape
@@ -1166,6 +1211,9 @@ def _dense_gemm(A2, B2):
     _lib.require_cuda_tensor(A2, "contraction")
     if B2.dtype != A2.dtype:
         raise RuntimeError("Contract(a,b): dtype mismatch %s vs %s" % (A2.dtype, B2.dtype))
+    shard = _dense_shard(M, N, K, A2)
+    if shard is not None:
+        return _dense_gemm_sharded(A2, B2, shard)
     out = torch.empty((M, N), device=A2.device, dtype=A2.dtype)
     if M * N == 0:
         return out
