@@ -389,7 +389,6 @@ class ResidentWorld:
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.seq = 0
         self.acquired = {}          # stream -> per-rank value known to have been acquired on it
-        self.pools = {}
         dist.barrier(group=group)
 
     def group_or_world(self):
@@ -568,8 +567,8 @@ def materialize(t):
         pull_sectors(t, [s for s in range(len(res.owner)) if not res.valid[s]])
         seq = rw.next_seq()
         res.slot.last_read = max(res.slot.last_read, seq)
+        t._arena = t._arena.clone()      # BEFORE the signal: once it is out, a peer may overwrite the slot ("push")
         rw.signal(seq)
-        t._arena = t._arena.clone()
         if res.slot.holder is not None and res.slot.holder() is t:
             res.slot.holder = None
     elif res.world > 1:
