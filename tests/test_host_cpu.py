@@ -447,3 +447,35 @@ def test_resident_collective_completion_world2_gloo(T):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_capture(T, tmp_path, monkeypatch):
+    """bench.py takes `roofline.traffic` from profiles/r02_ncu_raw_final.csv and refuses a capture that does not hold
+    the kernel the roofline names."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    got = bench.ncu_traffic("k_ggemm_f64_tma")
+    assert got is not None and 4.0e7 < got < 9.0e7            # operands once + parked partials, C stays in L2
+    rel = bench.ncu_traffic("k_relayout_segments")
+    assert rel is not None and 2.0e7 < rel < 4.0e7            # the source once: no index traffic
+    with pytest.raises(AssertionError):
+        bench.ncu_traffic("k_some_other_kernel")
+    monkeypatch.setattr(bench, "NCU_RAW", str(tmp_path / "missing.csv"))
+    assert bench.ncu_traffic("k_ggemm_f64_tma") is None
+
+
+def test_dense_shard_threshold(T, monkeypatch):
+    """Dense GEMMs are split over the ranks only above the flop threshold and when every rank gets a 64-row tile."""
+    import sys
+    U = sys.modules["tor10_b200.UniTensor"]
+    from tor10_b200 import parallel
+    x = torch.zeros(1, dtype=torch.float64)
+    assert U._dense_shard(2048, 2048, 2048, x) is None                     # sharding is off
+    monkeypatch.setitem(parallel._STATE, "enabled", True)
+    monkeypatch.setitem(parallel._STATE, "shard", (1, 4))
+    assert U._dense_shard(2048, 2048, 2048, x) == (1, 4)
+    assert U._dense_shard(128, 2048, 2048, x) is None                      # fewer than one tile of rows per rank
+    assert U._dense_shard(256, 256, 256, x) is None                        # below TOR10_DENSE_SHARD_MIN_GFLOP
+    assert U._dense_shard(2048, 2048, 2048, x.float()) is None             # fp64 only
