@@ -443,6 +443,9 @@ def resident_world(device=None):
         if dist.get_backend(_STATE["group"]) != "nccl":
             raise RuntimeError("tor10_b200.parallel: resident tensors need NVLink peer memory (NCCL process group)")
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if dist.get_world_size(_STATE["group"]) > 8:
+            raise RuntimeError("tor10_b200.parallel: resident tensors span the (at most 8) GPUs of ONE box; use a "
+                               "process group of that size")
         rw = ResidentWorld(_STATE["group"], device)
         _RES["world"] = rw
     return rw
