@@ -47,6 +47,7 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
   __shared__ unsigned s_maxr;          // largest squared |cos| of a rotated pair in this sweep (float bits)
   __shared__ T s_f2;
   __shared__ T s_sig[SV_MAX_N];
+  __shared__ T s_n2[SV_MAX_N];         // squared column norms, carried through the rotations of a sweep
   __shared__ int s_rank[SV_MAX_N];
   const SvdProb p = batch.p[blockIdx.x];
   const int m = p.m, n = p.n;
@@ -152,26 +153,28 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
   int sweep = 0;
   for (; sweep < SV_MAX_SWEEPS; ++sweep) {
     if (tid == 0) { s_rot = 0; s_maxr = 0u; }
+    // squared column norms: computed exactly once per sweep, then carried through the rotations (a rotation turns
+    // (alpha, beta, gamma) into c^2 alpha - 2cs gamma + s^2 beta and s^2 alpha + 2cs gamma + c^2 beta), so a round
+    // needs ONE dot product per pair instead of three
+    for (int c = grp; c < ne; c += ngrp) {
+      T a = 0;
+      for (int r = sub; r < m; r += SV_LPP) a += As[(size_t)c * ms + r] * As[(size_t)c * ms + r];
+#pragma unroll
+      for (int o = SV_LPP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
+      if (sub == 0) s_n2[c] = a;
+    }
     __syncthreads();
     for (int round = 0; round < nrounds; ++round) {
       for (int k = grp; k < npairs; k += ngrp) {
         const int pa = pairs[2 * (round * npairs + k)], pb = pairs[2 * (round * npairs + k) + 1];
         T* ap = As + (size_t)pa * ms;
         T* aq = As + (size_t)pb * ms;
-        T alpha = 0, beta = 0, gamma = 0;
+        const T alpha = s_n2[pa], beta = s_n2[pb];
+        T gamma = 0;
 #pragma unroll 4
-        for (int r = sub; r < m; r += SV_LPP) {
-          const T x = ap[r], y = aq[r];
-          alpha += x * x;
-          beta += y * y;
-          gamma += x * y;
-        }
+        for (int r = sub; r < m; r += SV_LPP) gamma += ap[r] * aq[r];
 #pragma unroll
-        for (int o = SV_LPP / 2; o > 0; o >>= 1) {
-          alpha += __shfl_xor_sync(gmask, alpha, o);
-          beta += __shfl_xor_sync(gmask, beta, o);
-          gamma += __shfl_xor_sync(gmask, gamma, o);
-        }
+        for (int o = SV_LPP / 2; o > 0; o >>= 1) gamma += __shfl_xor_sync(gmask, gamma, o);
         if (fmin(alpha, beta) >= floor2 && gamma * gamma > fmax(tol2 * alpha * beta, abs2)) {
           // Rotation: t = tan(theta) only has to be CLOSE to the annihilating tangent (what it leaves is removed by
           // the next sweep), so it is computed in fast fp32 arithmetic on operands scaled into range -- an fp64
@@ -217,6 +220,9 @@ k_svd_small(const T* __restrict__ A, T* __restrict__ U, T* __restrict__ S, T* __
             vq[r] = s * x + c * y;
           }
           if (sub == 0) {
+            const T cc = c * c, ss = s * s, cs2 = T(2) * c * s * gamma;
+            s_n2[pa] = fmax(cc * alpha - cs2 + ss * beta, T(0));
+            s_n2[pb] = fmax(ss * alpha + cs2 + cc * beta, T(0));
             s_rot = 1;
             const float abf = (float)(alpha * scale) * (float)(beta * scale);
             const float r2 = abf > 0.0f ? fminf(__fdividef(0.25f * gf * gf, abf), 1.0f) : 1.0f;
