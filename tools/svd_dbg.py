@@ -1,3 +1,8 @@
+"""In-kernel timers of the one-CTA Jacobi SVD (cycles / ns inside the sweep loop, sweeps) from a DEBUG build:
+    nvcc -DT10_SVD_DEBUG -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC --cudart shared \
+         -Iinclude -Itor10_b200/csrc -shared tor10_b200/csrc/svd_small.cu tor10_b200/csrc/blockmap.cu \
+         -o tools/bin/libsvddbg.so          (tools/bin is git-ignored; it travels to the GPU box with gpurun)
+    python tools/svd_dbg.py [library name under tools/bin]"""
 import ctypes as C, torch, json, sys, os
 lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", sys.argv[1] if len(sys.argv) > 1 else "libsvddbg.so"))
 dev = torch.device("cuda", 0)

@@ -1,5 +1,10 @@
 """Phase timeline of one rank's GEMM share with the T10_TRACE_PHASES debug build (tools/bin/libtor10_phases.so):
-CTA entry -> first piece start -> main loops -> fix-up done.  python tools/trace_phases.py [world]"""
+CTA entry -> first piece start -> main loops -> fix-up done.  python tools/trace_phases.py [world]
+Build the debug library first (every .cu with -DT10_TRACE_PHASES, linked into tools/bin/libtor10_phases.so):
+    for f in blockmap relayout permute_tma ggemm ggemm_tma ggemm_tf32 svd_small; do nvcc -DT10_TRACE_PHASES \
+        -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC --cudart shared -Iinclude \
+        -Itor10_b200/csrc -c tor10_b200/csrc/$f.cu -o /tmp/$f.o; done
+    nvcc -shared --cudart shared -o tools/bin/libtor10_phases.so /tmp/{blockmap,relayout,permute_tma,ggemm,ggemm_tma,ggemm_tf32,svd_small}.o"""
 import os, sys, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
