@@ -378,6 +378,35 @@ def test_plan_cache_is_a_bounded_lru(T):
     assert len(b) == 1 and b.get("big") is not None
 
 
+def test_pinned_objects_survive_eviction(T):
+    """graph.StaticLoop keeps what _plan.pinned_objects() returned: a later LRU eviction or clear_caches() must not
+    free a plan a captured graph still addresses by raw pointer."""
+    import gc
+    import weakref
+    from tor10_b200 import _plan
+
+    class P:
+        def plan_bytes(self):
+            return 8
+    saved = dict(_plan._CONTRACTS.d)
+    try:
+        p = P()
+        ref = weakref.ref(p)
+        _plan._CONTRACTS[("pin-test",)] = p
+        del p
+        pins = _plan.pinned_objects()
+        assert any(o is ref() for o in pins)
+        _plan.clear_caches()
+        gc.collect()
+        assert ref() is not None                     # held by the pins
+        del pins
+        gc.collect()
+        assert ref() is None
+    finally:
+        for k, v in saved.items():
+            _plan._CONTRACTS[k] = v
+
+
 def test_resident_ownership_and_fetch_plan(T):
     """Ownership propagates from a resident first operand; a rank pulls exactly the needed sectors it does
     not hold, grouped by owner, as whole 16-byte vectors."""

@@ -99,6 +99,21 @@ def clear_caches():
         par._STAGE.clear()
 
 
+def pinned_objects():
+    """Strong references to everything the caches hold right now: plans, relayouts, layouts, dense GEMM groups, the
+    warm state of the small SVD.  A captured CUDA graph (graph.StaticLoop) addresses their device tables by raw
+    pointer; holding this list keeps them alive after an LRU eviction or clear_caches()."""
+    import sys
+    pins = list(_LAYOUTS.values()) + list(_RELAYOUTS.values()) + list(_CONTRACTS.values())
+    mod = sys.modules.get(__package__ + ".UniTensor")
+    if mod is not None:
+        pins += list(mod._GEMM_GROUPS.values())
+    la = sys.modules.get(__package__ + ".linalg")
+    if la is not None:
+        pins += list(la._SVD_STATE.values())
+    return pins
+
+
 def _tensor_bytes(*ts):
     return sum(int(t.numel()) * t.element_size() for t in ts if t is not None)
 

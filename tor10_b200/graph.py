@@ -15,6 +15,7 @@ the one-CTA kernel) belongs outside the step function.
 """
 import torch
 
+from . import _plan
 from .UniTensor import UniTensor
 
 
@@ -57,6 +58,9 @@ class StaticLoop:
             _copy_state_(self.state, out[:n])
             self.outputs = tuple(_storage_of(o).clone() for o in out[n:])
         torch.cuda.synchronize()
+        # the graph addresses the device tables of the plans it used by raw pointer: keep them alive whatever the
+        # LRU caches evict later
+        self._pins = _plan.pinned_objects()
         self.steps = 0
 
     def __call__(self):
