@@ -829,6 +829,11 @@ class GemmGroup:
             if A.is_cuda and torch.cuda.is_current_stream_capturing():
                 # a captured upload re-reads its pinned source on every replay: keep it alive with the graph's maps
                 self._tma_pinned = getattr(self, "_tma_pinned", []) + [h]
+        if A.is_cuda and torch.cuda.is_current_stream_capturing():
+            # the graph addresses these maps by raw pointer: they must outlive their slot in the 16-entry cache
+            pinned = self.__dict__.setdefault("_tma_pinned", [])
+            if not any(p is d_maps for p in pinned):
+                pinned.append(d_maps)
         if self.sk_parked and A.is_cuda and torch.cuda.is_current_stream_capturing():
             raise RuntimeError("tor10_b200: this contraction cuts tiles across CTAs (stream-K flags carry a per-launch "
                                "epoch) and cannot be captured into a CUDA graph; run it eagerly")
