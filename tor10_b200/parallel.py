@@ -319,10 +319,11 @@ class Residency:
 
 
 class _Slot:
-    __slots__ = ("pool", "index", "holder", "last_read")
+    __slots__ = ("pool", "index", "holder", "last_read", "pull_args")
 
     def __init__(self, pool, index):
         self.pool, self.index, self.holder, self.last_read = pool, index, None, 0
+        self.pull_args = {}          # cached argument arrays of pull_sectors (they hold this slot's peer addresses)
 
     def tensor(self):
         return self.pool.bufs[self.index]
@@ -480,9 +481,6 @@ def fetch_plan(layout, res, needed):
     return out
 
 
-_PULL_ARGS = {}
-
-
 def pull_sectors(t, needed):
     """Make the `needed` sectors of resident tensor t valid in this rank's arena: one pull kernel over the owners'
     NVLink peer mappings (after acquiring their progress).  No-op for sectors already here."""
@@ -500,10 +498,12 @@ def pull_sectors(t, needed):
         need[o] = res.seq
     rw.wait(need)
     # one launch for (up to 64) slices: neighbouring sectors of one owner travel as one slice; the argument arrays are
-    # cached per slot and request (a "pull" transport asks for the same sectors every step)
-    key = (id(res.slot), tuple(needed) if not isinstance(needed, range) else (needed.start, needed.stop),
+    # cached ON the slot per request (a "pull" transport asks for the same sectors every step; the cache dies with
+    # the slot whose peer addresses it holds)
+    key = (tuple(needed) if not isinstance(needed, range) else ("range", needed.start, needed.stop, needed.step),
            res.owner.tobytes())
-    args = _PULL_ARGS.get(key)
+    cache = res.slot.pull_args
+    args = cache.get(key)
     if args is None:
         segs = []
         for o, rs in sorted(plan.items(), key=lambda kv: (kv[0] - res.rank) % res.world):   # start with the next rank
@@ -518,9 +518,9 @@ def pull_sectors(t, needed):
             n = len(part)
             args.append((n, (C.c_void_p * n)(*[res.slot.peer_ptr(o) for o, _, _ in part]),
                          (C.c_int64 * n)(*[a for _, a, _ in part]), (C.c_int64 * n)(*[b for _, _, b in part])))
-        if len(_PULL_ARGS) > 256:
-            _PULL_ARGS.clear()
-        _PULL_ARGS[key] = args
+        if len(cache) > 64:
+            cache.clear()
+        cache[key] = args
     arena = t._arena
     for n, ptrs, los, his in args:
         _lib.check(_lib.load().t10_gather_peers(_lib.dtype_code(arena.dtype), arena.data_ptr(), n, ptrs, los, his,
