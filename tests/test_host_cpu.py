@@ -508,3 +508,66 @@ def test_dense_shard_threshold(T, monkeypatch):
     assert U._dense_shard(128, 2048, 2048, x) is None                      # fewer than one tile of rows per rank
     assert U._dense_shard(256, 256, 256, x) is None                        # below TOR10_DENSE_SHARD_MIN_GFLOP
     assert U._dense_shard(2048, 2048, 2048, x.float()) is None             # fp64 only
+
+
+def test_pull_sectors_host_logic(T, monkeypatch):
+    """parallel.pull_sectors on host memory with a stand-in for the gather kernel: the right slices of the right
+    owners arrive, neighbouring sectors of one owner merge into one slice, the argument arrays are cached on the slot
+    (a list request and a range request with the same two numbers do not share an entry), validity and the slot's
+    write-after-read bound are updated.  (The kernel itself: tests/test_gpu_multi.py.)"""
+    import ctypes as C
+    from tor10_b200 import parallel, _lib
+
+    class L:
+        arena_off = np.array([0, 16, 48, 64, 96])
+        rows = np.array([2, 4, 2, 4, 2])
+        ld = np.array([8, 8, 8, 8, 8])
+    n = 112
+    peers = [np.full(n, 100.0 * (r + 1)) + np.arange(n) for r in range(3)]          # rank r's copy of the arena
+    mine = torch.zeros(n, dtype=torch.float64)
+
+    class Pool:
+        bufs = [mine]
+        peer_ptrs = [[p.ctypes.data for p in peers]]
+    slot = parallel._Slot(Pool(), 0)
+    owner = np.array([0, 1, 1, 2, -1])
+    res = parallel.Residency(3, 0, owner, 5, slot)
+
+    class Tns:
+        _res, _layout, _arena = res, L, mine
+    calls = []
+
+    class Lib:
+        def t10_gather_peers(self, dt, dst, nseg, ptrs, los, his, st):
+            out = np.ctypeslib.as_array((C.c_double * n).from_address(dst))
+            for i in range(nseg):
+                src = np.ctypeslib.as_array((C.c_double * n).from_address(ptrs[i]))
+                out[los[i]:his[i]] = src[los[i]:his[i]]
+            calls.append([(ptrs[i], los[i], his[i]) for i in range(nseg)])
+            return 0
+
+    class RW:
+        world, rank, seq = 3, 0, 9
+        waited = []
+
+        def wait(self, need):
+            self.waited.append(list(need))
+    rw = RW()
+    monkeypatch.setattr(parallel, "resident_world", lambda device=None: rw)
+    monkeypatch.setattr(_lib, "load", lambda: Lib())
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
+    parallel.pull_sectors(Tns, [0, 1, 2, 4])             # 0 and 4 are valid here already; 1 and 2 live on rank 1
+    assert rw.waited == [[0, 5, 0]]
+    assert calls == [[(peers[1].ctypes.data, 16, 64)]]                       # sectors 1+2: one slice
+    assert np.array_equal(mine.numpy()[16:64], peers[1][16:64]) and mine.numpy()[64:].sum() == 0
+    assert res.valid.tolist() == [True, True, True, False, True] and slot.last_read == 10
+    assert len(slot.pull_args) == 1
+    parallel.pull_sectors(Tns, [0, 1, 2, 4])             # nothing left to pull: no wait, no launch
+    assert len(calls) == 1 and len(rw.waited) == 1
+    parallel.pull_sectors(Tns, range(3, 4))              # sector 3 from rank 2
+    assert calls[-1] == [(peers[2].ctypes.data, 64, 96)] and res.valid.all()
+    assert np.array_equal(mine.numpy()[64:96], peers[2][64:96])
+    assert set(k[0] for k in slot.pull_args) == {(0, 1, 2, 4), ("range", 3, 4, 1)}
+    Tns._res = parallel.Residency(3, 0, owner, 6, None)                     # not in peer-readable memory any more
+    with pytest.raises(RuntimeError):
+        parallel.pull_sectors(Tns, [3])
