@@ -571,3 +571,62 @@ def test_pull_sectors_host_logic(T, monkeypatch):
     Tns._res = parallel.Residency(3, 0, owner, 6, None)                     # not in peer-readable memory any more
     with pytest.raises(RuntimeError):
         parallel.pull_sectors(Tns, [3])
+
+
+def test_materialize_and_ring_reuse_order(T, monkeypatch):
+    """parallel.materialize: the private copy is taken BEFORE the read is published (afterwards a pushing peer may
+    overwrite the slot), the slot's write-after-read bound moves to the published value and the slot is released;
+    ArenaPool.acquire gathers a tensor still living in the slot it hands out."""
+    import weakref
+    from tor10_b200 import parallel
+    log = []
+
+    class Arena:
+        def clone(self):
+            log.append("clone")
+            return self
+
+    class RW:
+        world, rank, seq = 2, 0, 4
+
+        def next_seq(self):
+            self.seq += 1
+            return self.seq
+
+        def signal(self, v):
+            log.append(("signal", v))
+
+        def wait(self, need):
+            log.append(("wait", list(need)))
+    rw = RW()
+    monkeypatch.setattr(parallel, "resident_world", lambda device=None: rw)
+
+    class Pool:
+        depth = 2
+    pool = Pool()
+    pool.slots = [parallel._Slot(pool, 0), parallel._Slot(pool, 1)]
+    pool.turn = 0
+    owner = np.array([0, -1])
+
+    class Tns:
+        def __init__(self, slot):
+            self._res = parallel.Residency(2, 0, owner, 3, slot)
+            self._arena, self._blocks, self._layout = Arena(), "blocks", None
+
+        def _materialize(self):
+            parallel.materialize(self)
+    t = Tns(pool.slots[0])
+    pool.slots[0].holder = weakref.ref(t)
+    parallel.materialize(t)
+    assert log == ["clone", ("signal", 5)]                  # every sector valid here: no pull, no wait
+    assert t._res is None and t._blocks is None and pool.slots[0].holder is None and pool.slots[0].last_read == 5
+    parallel.materialize(t)                                  # idempotent
+    assert len(log) == 2
+    # ring reuse: slot 0 is free, slot 1 still holds a live tensor -> it is gathered out when the ring comes round
+    u = Tns(pool.slots[1])
+    pool.slots[1].holder = weakref.ref(u)
+    s0, war0 = parallel.ArenaPool.acquire(pool)
+    assert s0 is pool.slots[0] and war0 == 5 and len(log) == 2
+    s1, war1 = parallel.ArenaPool.acquire(pool)
+    assert s1 is pool.slots[1] and u._res is None and log[2:] == ["clone", ("signal", 6)] and s1.holder is None
+    assert pool.turn == 0
