@@ -376,6 +376,19 @@ def test_plan_cache_is_a_bounded_lru(T):
     assert b.get("a") is None and b.bytes == 20
     b["big"] = P(1000)                                  # a single entry over the budget is kept (it is in use)
     assert len(b) == 1 and b.get("big") is not None
+    # GEMM groups and contraction plans report the device tables they hold (stream-K workspace, tensor maps)
+
+    class G:
+        def __init__(self):
+            self.ws = torch.zeros(10, dtype=torch.float64)
+            self.maps = {1: torch.zeros(256, dtype=torch.uint8), 2: "x"}
+            self.keep = [torch.zeros(3, dtype=torch.int32), None]
+            self.n = 5
+    assert _plan._owned_tensor_bytes(G()) == 80 + 256 + 12
+    import sys
+    U = sys.modules["tor10_b200.UniTensor"]
+    assert isinstance(U._GEMM_GROUPS, _plan.LRU) and hasattr(_plan.GemmGroup, "plan_bytes") \
+        and hasattr(_plan.ContractPlan, "plan_bytes")
 
 
 def test_pinned_objects_survive_eviction(T):

@@ -1154,7 +1154,7 @@ def Load(filename):
     return tmp
 
 
-_GEMM_GROUPS = {}
+_GEMM_GROUPS = _plan.LRU(_plan._CACHE_ENTRIES, _plan._CACHE_BYTES)      # dense GEMM groups per shape (bounded: ADVICE r1)
 
 
 _DENSE_SHARD_MIN_FLOP = float(os.environ.get("TOR10_DENSE_SHARD_MIN_GFLOP", "2")) * 1e9

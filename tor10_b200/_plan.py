@@ -118,6 +118,19 @@ def _tensor_bytes(*ts):
     return sum(int(t.numel()) * t.element_size() for t in ts if t is not None)
 
 
+def _owned_tensor_bytes(obj):
+    """Bytes of the torch tensors an object holds directly or in a dict / list / tuple attribute (its device tables)."""
+    n = 0
+    for v in vars(obj).values():
+        if isinstance(v, torch.Tensor):
+            n += int(v.numel()) * v.element_size()
+        elif isinstance(v, dict):
+            n += sum(int(x.numel()) * x.element_size() for x in v.values() if isinstance(x, torch.Tensor))
+        elif isinstance(v, (list, tuple)):
+            n += sum(int(x.numel()) * x.element_size() for x in v if isinstance(x, torch.Tensor))
+    return n
+
+
 def _dev_index(device):
     device = torch.device(device)
     return torch.cuda.current_device() if device.index is None else device.index
@@ -801,6 +814,10 @@ class GemmGroup:
         self.sk_parked = nparked
         return True
 
+    def plan_bytes(self):
+        """Tile / piece tables, the stream-K workspace of parked partials (~10 MB), cached tensor maps."""
+        return _owned_tensor_bytes(self)
+
     def run_streamk(self, A, B, Cc):
         self.sk_epoch = self.sk_epoch % 2000000000 + 1
         st = self._sk_static
@@ -1195,6 +1212,16 @@ def _make_out(self, Cc):
     return UniTensor._from_template(tpl, Cc)
 
 
+def _contract_plan_bytes(self):
+    """The GEMM group's tables and workspace plus the peer-source segment tables (the relayouts are entries of their
+    own cache; result rings are result storage, not plan memory)."""
+    n = self.gemm.plan_bytes() if getattr(self, "gemm", None) is not None else 0
+    for seg, _ in getattr(self, "_res_segs", {}).values():
+        n += int(seg.numel()) * seg.element_size()
+    return n
+
+
+ContractPlan.plan_bytes = _contract_plan_bytes
 ContractPlan._make_out = _make_out
 ContractPlan._out_tpl = None
 ContractPlan._pool = False
