@@ -643,3 +643,34 @@ def test_materialize_and_ring_reuse_order(T, monkeypatch):
     s1, war1 = parallel.ArenaPool.acquire(pool)
     assert s1 is pool.slots[1] and u._res is None and log[2:] == ["clone", ("signal", 6)] and s1.holder is None
     assert pool.turn == 0
+
+
+def test_resident_wait_is_skipped_when_already_acquired(T, monkeypatch):
+    """ResidentWorld.wait launches the acquire kernel only for progress values the current stream has not acquired
+    yet: nothing to wait for, this rank's own (stream-ordered) operations and repeated waits cost no launch."""
+    from tor10_b200 import parallel, _lib
+    rw = object.__new__(parallel.ResidentWorld)
+    rw.world, rw.rank, rw.seq, rw.acquired = 3, 1, 7, {}
+    rw.word_ptrs = None
+
+    class Err:
+        def data_ptr(self):
+            return 0
+    rw.err = Err()
+    calls = []
+
+    class Lib:
+        def t10_wait_flags(self, n, ptrs, need, timeout_ms, err, st):
+            calls.append(([int(need[i]) for i in range(n)], timeout_ms, st))
+            return 0
+    stream = [11]
+    monkeypatch.setattr(_lib, "load", lambda: Lib())
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: stream[0])
+    assert rw.wait([0, 0, 0]) is False and not calls
+    assert rw.wait([0, 7, 0]) is False and not calls            # own operations up to seq: stream order
+    assert rw.wait([5, 0, 0]) is True and calls[-1][0] == [5, 0, 0] and calls[-1][1] == parallel.WAIT_TIMEOUT_MS
+    assert rw.wait([5, 3, 0]) is False and len(calls) == 1      # known on this stream
+    assert rw.wait([4, 0, 6]) is True and calls[-1][0] == [4, 0, 6]
+    assert rw.acquired[11] == [5, 7, 6]
+    stream[0] = 12                                              # another stream has acquired nothing yet
+    assert rw.wait([5, 0, 0]) is True and len(calls) == 3 and calls[-1][2] == 12
