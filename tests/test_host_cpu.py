@@ -674,3 +674,39 @@ def test_resident_wait_is_skipped_when_already_acquired(T, monkeypatch):
     assert rw.acquired[11] == [5, 7, 6]
     stream[0] = 12                                              # another stream has acquired nothing yet
     assert rw.wait([5, 0, 0]) is True and len(calls) == 3 and calls[-1][2] == 12
+
+
+def test_resident_segments_pick_the_owner_arena(T):
+    """_plan._resident_segments: the `source` column of a relayout's segment table is 0 for pieces whose source
+    sector is valid here and k > 0 for the k-th foreign owner (read through its NVLink mapping inside the copy);
+    zero-fill pieces (src < 0) stay local; cached per (owner, valid) state."""
+    from tor10_b200 import _plan, parallel
+
+    class M:
+        arena_off = np.array([0, 100, 200, 300])
+
+    class Rel:
+        pass
+    rel = Rel()
+    rel.M = M
+    #                        dst  src  len source
+    rel.d_seg = torch.tensor([[0, 10, 8, 0], [8, 150, 8, 0], [16, 250, 4, 0], [20, 305, 6, 0], [26, -1, 2, 0],
+                              [28, 199, 1, 0]], dtype=torch.int32)
+
+    class Plan:
+        _res_segs = {}
+    owner = np.array([0, 2, 1, 2])
+    res = parallel.Residency(3, 0, owner, 1, None)            # rank 0 holds sector 0 only
+
+    class Tns:
+        _res = res
+    seg, foreign = _plan._resident_segments(Plan, "a", rel, Tns)
+    assert foreign == [1, 2]
+    assert seg[:, 3].tolist() == [0, 2, 1, 2, 0, 2]           # sector 1 and 3 from rank 2 (2nd foreign), 2 from rank 1
+    assert seg[:, :3].tolist() == rel.d_seg[:, :3].tolist() and rel.d_seg[:, 3].sum() == 0    # the plan's table is untouched
+    assert _plan._resident_segments(Plan, "a", rel, Tns)[0] is seg                             # cached
+    res.valid[1] = True                                        # sector 1 has been pulled: read locally from now on
+    seg2, foreign2 = _plan._resident_segments(Plan, "a", rel, Tns)
+    assert seg2[:, 3].tolist() == [0, 0, 1, 2, 0, 0] and foreign2 == [1, 2]
+    rel.d_seg = None
+    assert _plan._resident_segments(Plan, "a", rel, Tns) is None
